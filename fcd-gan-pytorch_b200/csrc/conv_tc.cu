@@ -1,0 +1,396 @@
+// conv_tc.cu — tcgen05 + TMA implicit-GEMM convolution (forward / stride-1 dgrad) for sm_100a.
+//
+// Replaces the nn.Conv2d calls of the reference networks (Module.py:26,29,155,177,180 and, through
+// dgrad, their autograd backward).  GEMM view:  M = output pixels, N = output channels,
+// K = taps x input channels.
+//
+//   * One CTA tile = 8 x 16 output pixels of one image (M = 128) x BLOCK_N output channels.
+//   * For every (tap, 64-channel chunk) k-block a TMA box {64 ch, 16 w, 8 h, 1 n} of the NHWC input,
+//     shifted by the tap offset, lands in 128B-swizzled shared memory: exactly the K-major A operand
+//     of a 128 x 64 UMMA tile.  Out-of-bounds rows/columns are zero-filled by TMA = the conv padding.
+//   * Accumulators live in TMEM (double buffered, BLOCK_N fp32 columns each); one elected thread
+//     issues tcgen05.mma; with split-bf16 operands three MMAs per k-step (hi*hi + lo*hi + hi*lo)
+//     recover fp32-class products.
+//   * Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue
+//     (tcgen05.ld -> +bias -> fp32 NHWC store, optional per-channel sum / sum-of-squares for BN).
+//   * Persistent: grid = #SMs, static round-robin over tiles.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "fcd_common.cuh"
+#include "fcd_tc.cuh"
+
+namespace fcd {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int BLOCK_M = TILE_H * TILE_W;  // 128
+constexpr int BLOCK_K = 64;               // bf16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+template <int BLOCK_N, bool SPLIT>
+struct Cfg {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
+    static constexpr int SMEM_BUDGET = 200 * 1024;
+    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for 32..256
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct ConvTcParams {
+    const float* bias;
+    float* z;
+    double* stat_sum;
+    double* stat_sqsum;
+    int z_ld;
+    int N, OH, OW;       // output spatial dims (== input dims for stride 1 "same")
+    int Cin_p, Cout_p;
+    int KH, KW, pad;
+    int tiles_h, tiles_w, n_blocks;
+    long long total_tiles;
+};
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const ConvTcParams p) {
+    using C = Cfg<BLOCK_N, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full = empty_bar + C::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x_hi);
+        tma_prefetch_desc(&map_w_hi);
+        if (SPLIT) {
+            tma_prefetch_desc(&map_x_lo);
+            tma_prefetch_desc(&map_w_lo);
+        }
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int cchunks = p.Cin_p / BLOCK_K;
+    const int num_kb = p.KH * p.KW * cchunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                long long t = tile;
+                const int nblk = static_cast<int>(t % p.n_blocks);
+                t /= p.n_blocks;
+                const int tw = static_cast<int>(t % p.tiles_w);
+                t /= p.tiles_w;
+                const int th = static_cast<int>(t % p.tiles_h);
+                const int n = static_cast<int>(t / p.tiles_h);
+                const int h0 = th * TILE_H - p.pad, w0 = tw * TILE_W - p.pad;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / cchunks, cc = kb - tap * cchunks;
+                    const int r = tap / p.KW, s = tap - r * p.KW;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                    tma_load_4d(st, &map_x_hi, &full_bar[stage], cc * BLOCK_K, w0 + s, h0 + r, n);
+                    tma_load_3d(st + C::A_BYTES * C::PLANES, &map_w_hi, &full_bar[stage], cc * BLOCK_K,
+                                nblk * BLOCK_N, tap);
+                    if (SPLIT) {
+                        tma_load_4d(st + C::A_BYTES, &map_x_lo, &full_bar[stage], cc * BLOCK_K, w0 + s, h0 + r, n);
+                        tma_load_3d(st + C::A_BYTES * 2 + C::B_BYTES, &map_w_lo, &full_bar[stage], cc * BLOCK_K,
+                                    nblk * BLOCK_N, tap);
+                    }
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t b_hi = a_hi + C::A_BYTES * C::PLANES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da_hi = make_smem_desc(a_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                        const uint64_t db_hi = make_smem_desc(b_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                        umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (SPLIT) {
+                            const uint64_t da_lo =
+                                make_smem_desc(a_hi + C::A_BYTES + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                            const uint64_t db_lo =
+                                make_smem_desc(b_hi + C::B_BYTES + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int lh = row / TILE_W, lw = row - lh * TILE_W;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        __shared__ float s_red[4][2][32];  // per-epilogue-warp staging for the BN statistics
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            long long t = tile;
+            const int nblk = static_cast<int>(t % p.n_blocks);
+            t /= p.n_blocks;
+            const int tw = static_cast<int>(t % p.tiles_w);
+            t /= p.tiles_w;
+            const int th = static_cast<int>(t % p.tiles_h);
+            const int n = static_cast<int>(t / p.tiles_h);
+            const int oh = th * TILE_H + lh, ow = tw * TILE_W + lw;
+            const bool valid = (oh < p.OH) && (ow < p.OW);
+            float* zrow = p.z + (static_cast<size_t>(n) * p.OH * p.OW + static_cast<size_t>(oh) * p.OW + ow) * p.z_ld +
+                          nblk * BLOCK_N;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + acc * BLOCK_N + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    f[j] = __uint_as_float(v[j]);
+                    if (p.bias) f[j] += __ldg(p.bias + nblk * BLOCK_N + c + j);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(zrow + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+                if (p.stat_sum) {
+                    // column sums over this warp's 32 pixels, then one double atomic per channel
+                    const int ew = warp - EPI_WARP0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float a = valid ? f[j] : 0.f;
+                        float b = a * a;
+                        a = warp_sum(a);
+                        b = warp_sum(b);
+                        if (lane == j) {
+                            s_red[ew][0][j] = a;
+                            s_red[ew][1][j] = b;
+                        }
+                    }
+                    __syncwarp();
+                    atomicAdd(p.stat_sum + nblk * BLOCK_N + c + lane, static_cast<double>(s_red[ew][0][lane]));
+                    atomicAdd(p.stat_sqsum + nblk * BLOCK_N + c + lane, static_cast<double>(s_red[ew][1][lane]));
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// 4D NHWC bf16 activation map: dims {C, W, H, N}, box {64, TILE_W, TILE_H, 1}, 128B swizzle, zero fill.
+int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
+                  int box_h) {
+    auto enc = get_encode_fn();
+    if (!enc) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        return FCD_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = box_c * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d N=%d ld=%d)", (int)r, C, W, H,
+                  N, ld);
+        return FCD_ERR_CUDA;
+    }
+    return FCD_OK;
+}
+
+// 3D packed weight map: dims {cols, rows, taps}, box {64, box_rows, 1}.
+int make_wgt_tmap(CUtensorMap* m, const void* base, int cols, int rows, int taps, int box_cols, int box_rows) {
+    auto enc = get_encode_fn();
+    if (!enc) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        return FCD_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled(weight) failed: %d (cols=%d rows=%d taps=%d)", (int)r, cols,
+                  rows, taps);
+        return FCD_ERR_CUDA;
+    }
+    return FCD_OK;
+}
+
+bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
+    return stride == 1 && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH >= 1 && KW >= 1 && KH <= 9 && KW <= 9;
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh,
+                          const CUtensorMap& mwl, const ConvTcParams& p, cudaStream_t stream) {
+    using C = Cfg<BLOCK_N, SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FCD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES));
+        attr_set = true;
+    }
+    long long grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_tc_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
+                  const float* bias, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
+                  int pad, double* stat_sum, double* stat_sqsum, cudaStream_t stream) {
+    const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
+    FCD_CHECK_ARG(OH > 0 && OW > 0, "conv2d_fwd_tc: empty output");
+    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0, "conv2d_fwd_tc: pitches must keep 16-byte alignment");
+    const bool split = (x_lo != nullptr) && (w_lo != nullptr);
+    const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
+
+    CUtensorMap mxh, mxl, mwh, mwl;
+    int rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, BLOCK_K, TILE_W, TILE_H))) return rc;
+    if ((rc = make_wgt_tmap(&mwh, w_hi, Cin_p, Cout_p, KH * KW, BLOCK_K, block_n))) return rc;
+    if (split) {
+        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, BLOCK_K, TILE_W, TILE_H))) return rc;
+        if ((rc = make_wgt_tmap(&mwl, w_lo, Cin_p, Cout_p, KH * KW, BLOCK_K, block_n))) return rc;
+    } else {
+        mxl = mxh;
+        mwl = mwh;
+    }
+    ConvTcParams p;
+    p.bias = bias;
+    p.z = z;
+    p.stat_sum = stat_sum;
+    p.stat_sqsum = stat_sqsum;
+    p.z_ld = z_ld;
+    p.N = N;
+    p.OH = OH;
+    p.OW = OW;
+    p.Cin_p = Cin_p;
+    p.Cout_p = Cout_p;
+    p.KH = KH;
+    p.KW = KW;
+    p.pad = pad;
+    p.tiles_h = ceil_div(OH, TILE_H);
+    p.tiles_w = ceil_div(OW, TILE_W);
+    p.n_blocks = Cout_p / block_n;
+    p.total_tiles = 1LL * N * p.tiles_h * p.tiles_w * p.n_blocks;
+    if (block_n == 128)
+        return split ? launch_conv_tc<128, true>(mxh, mxl, mwh, mwl, p, stream)
+                     : launch_conv_tc<128, false>(mxh, mxl, mwh, mwl, p, stream);
+    return split ? launch_conv_tc<64, true>(mxh, mxl, mwh, mwl, p, stream)
+                 : launch_conv_tc<64, false>(mxh, mxl, mwh, mwl, p, stream);
+}
+
+}  // namespace fcd

@@ -1,0 +1,131 @@
+// probe_tc.cu — single-CTA tcgen05 probe used by scripts/probe_umma.py and tests/test_umma_probe.py.
+// It fills shared memory with the 128B-swizzle pattern TMA would produce, issues UMMAs with a
+// caller-chosen start-address shift / base_offset / major-ness, and writes the fp32 accumulator back,
+// so the descriptor semantics the convolution kernels rely on (row-shifted "halo" views of one staged
+// tile; MN-major operands for wgrad) are pinned by measurement rather than by reading of the ISA text.
+#include "fcd_common.cuh"
+#include "fcd_tc.cuh"
+
+namespace fcd {
+using namespace tc;
+namespace {
+
+// smem image: rows of 128 bytes (64 bf16), 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
+__device__ void fill_swizzled(uint8_t* dst, const __nv_bfloat16* src, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        const int r = i >> 3, c = i & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * 64 + c * 8);
+        *reinterpret_cast<uint4*>(dst + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+}
+
+struct ProbeParams {
+    const __nv_bfloat16* a;  // [a_blocks][a_rows][64]
+    const __nv_bfloat16* b;  // [b_blocks][b_rows][64]
+    float* d;                // [128][n]
+    int a_rows, b_rows, a_blocks, b_blocks;
+    int mn_major;            // 0: K-major A and B; 1: MN-major A and B
+    int n;                   // UMMA N (multiple of 16, <= 256)
+    int ksteps;              // number of K=16 UMMAs
+    int a_shift_rows, a_base_offset;
+    int b_shift_rows, b_base_offset;
+    int a_sbo, b_sbo;        // stride-byte-offset overrides (0 = 1024)
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_holder;
+    const int warp = threadIdx.x >> 5;
+
+    uint8_t* sa = smem;
+    const int a_block_bytes = p.a_rows * 128;
+    uint8_t* sb = sa + ((p.a_blocks * a_block_bytes + 1023) & ~1023);
+    const int b_block_bytes = p.b_rows * 128;
+    for (int blk = 0; blk < p.a_blocks; ++blk)
+        fill_swizzled(sa + blk * a_block_bytes, p.a + static_cast<size_t>(blk) * p.a_rows * 64, p.a_rows);
+    for (int blk = 0; blk < p.b_blocks; ++blk)
+        fill_swizzled(sb + blk * b_block_bytes, p.b + static_cast<size_t>(blk) * p.b_rows * 64, p.b_rows);
+    // generic-proxy writes must be visible to the async (tensor-core) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_holder, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, p.n, p.mn_major, p.mn_major);
+        const uint32_t a0 = smem_u32(sa) + p.a_shift_rows * 128;
+        const uint32_t b0 = smem_u32(sb) + p.b_shift_rows * 128;
+        const uint32_t a_sbo = p.a_sbo ? p.a_sbo : 1024, b_sbo = p.b_sbo ? p.b_sbo : 1024;
+        for (int k = 0; k < p.ksteps; ++k) {
+            uint64_t da, db;
+            if (!p.mn_major) {
+                // K-major: 16 bf16 = 32 bytes further along the 128-byte row
+                da = make_smem_desc(a0 + k * 32, 16, a_sbo, kSwizzle128, p.a_base_offset);
+                db = make_smem_desc(b0 + k * 32, 16, b_sbo, kSwizzle128, p.b_base_offset);
+            } else {
+                // MN-major: K runs over rows; 16 rows = 2048 bytes; LBO = distance between 64-wide MN blocks
+                da = make_smem_desc(a0 + k * 2048, a_block_bytes, a_sbo, kSwizzle128, p.a_base_offset);
+                db = make_smem_desc(b0 + k * 2048, b_block_bytes, b_sbo, kSwizzle128, p.b_base_offset);
+            }
+            umma_f16(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+
+    const int row = warp * 32 + (threadIdx.x & 31);
+    for (int c = 0; c < p.n; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + c + (static_cast<uint32_t>(warp * 32) << 16), v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) p.d[static_cast<size_t>(row) * p.n + c + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace
+}  // namespace fcd
+
+using namespace fcd;
+
+extern "C" int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks,
+                                    int b_blocks, int mn_major, int n, int ksteps, int a_shift_rows,
+                                    int a_base_offset, int b_shift_rows, int b_base_offset, int a_sbo, int b_sbo,
+                                    void* stream) {
+    FCD_CHECK_ARG(a && b && d, "umma_probe: null pointer");
+    FCD_CHECK_ARG(n % 16 == 0 && n >= 16 && n <= 256, "umma_probe: bad N");
+    ProbeParams p;
+    p.a = (const __nv_bfloat16*)a;
+    p.b = (const __nv_bfloat16*)b;
+    p.d = d;
+    p.a_rows = a_rows; p.b_rows = b_rows; p.a_blocks = a_blocks; p.b_blocks = b_blocks;
+    p.mn_major = mn_major; p.n = n; p.ksteps = ksteps;
+    p.a_shift_rows = a_shift_rows; p.a_base_offset = a_base_offset;
+    p.b_shift_rows = b_shift_rows; p.b_base_offset = b_base_offset;
+    p.a_sbo = a_sbo; p.b_sbo = b_sbo;
+    const int smem = ((a_blocks * a_rows * 128 + 1023) & ~1023) + b_blocks * b_rows * 128 + 2048;
+    FCD_CHECK_ARG(smem <= 200 * 1024, "umma_probe: operands do not fit shared memory");
+    FCD_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    umma_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}

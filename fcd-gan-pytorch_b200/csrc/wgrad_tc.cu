@@ -1,0 +1,324 @@
+// wgrad_tc.cu — tcgen05 weight-gradient GEMM for stride-1 convolutions (nn.Conv2d backward w.r.t. weight,
+// i.e. autograd of Module.py:26,29,155,177,180).
+//
+//   dW[tap][ci][co] = sum_{pixels} x[pixel + tap][ci] * dz[pixel][co]
+//
+// GEMM view: M = (tap, ci) "row groups" of 64 input channels, two per 128-row UMMA; N = co;
+// K = output pixels.  Both operands are NHWC so the reduction dimension (pixels) is the strided one:
+// the UMMA descriptors are MN-major, the TMA boxes {64 ch, 16 w, 4 h} land as [64 pixel rows][128 B].
+// Each CTA owns one (M-block, N-block) accumulator in TMEM over a contiguous range of pixel tiles
+// (split-K) and adds it into an fp32 workspace [tap][ci][co]; a small kernel then scatters the
+// workspace into the OIHW gradient torch expects.
+#include <cuda.h>
+
+#include "fcd_common.cuh"
+#include "fcd_tc.cuh"
+
+namespace fcd {
+using namespace tc;
+
+int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
+                  int box_h);
+
+namespace {
+
+constexpr int PT_H = 4, PT_W = 16;        // pixel tile = 64 pixels = K per stage
+constexpr int SUB_BYTES = 64 * 128;       // one [64 px][64 ch] bf16 sub-tile
+constexpr int NUM_THREADS = 192;
+
+template <int BLOCK_N, bool SPLIT>
+struct WCfg {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int NB = BLOCK_N / 64;
+    static constexpr int A_BYTES = 2 * SUB_BYTES;            // per plane
+    static constexpr int B_BYTES = NB * SUB_BYTES;           // per plane
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = BLOCK_N;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct WgradParams {
+    float* ws;            // [R*64][Cout_p] fp32, zero-initialised by the host wrapper
+    int N, OH, OW;
+    int Cin_p, Cout_p, KH, KW, pad;
+    int cchunks, R;       // row groups = taps * cchunks
+    int m_blocks, n_blocks, ksplit;
+    int tiles_h, tiles_w;
+    long long total_pt, pt_per_split;
+};
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                const WgradParams p) {
+    using C = WCfg<BLOCK_N, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* done_bar = empty_bar + C::STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int nb = item % p.n_blocks;
+    const int mb = item / p.n_blocks;
+    const long long pt_begin = ks * p.pt_per_split;
+    long long pt_end = pt_begin + p.pt_per_split;
+    if (pt_end > p.total_pt) pt_end = p.total_pt;
+    const int rg0 = 2 * mb, rg1 = (2 * mb + 1 < p.R) ? 2 * mb + 1 : 2 * mb;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x_hi);
+        tma_prefetch_desc(&map_g_hi);
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, C::TMEM_COLS < 32 ? 32 : C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int tapv[2], cbv[2];
+            tapv[0] = rg0 / p.cchunks; cbv[0] = rg0 % p.cchunks;
+            tapv[1] = rg1 / p.cchunks; cbv[1] = rg1 % p.cchunks;
+            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+                long long t = pt;
+                const int tw = static_cast<int>(t % p.tiles_w); t /= p.tiles_w;
+                const int th = static_cast<int>(t % p.tiles_h);
+                const int n = static_cast<int>(t / p.tiles_h);
+                const int h0 = th * PT_H, w0 = tw * PT_W;
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* st = smem + stage * C::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int r = tapv[sub] / p.KW, s = tapv[sub] % p.KW;
+                    tma_load_4d(st + sub * SUB_BYTES, &map_x_hi, &full_bar[stage], cbv[sub] * 64, w0 + s - p.pad,
+                                h0 + r - p.pad, n);
+                    if (SPLIT)
+                        tma_load_4d(st + C::A_BYTES + sub * SUB_BYTES, &map_x_lo, &full_bar[stage], cbv[sub] * 64,
+                                    w0 + s - p.pad, h0 + r - p.pad, n);
+                }
+                uint8_t* sb = st + C::A_BYTES * C::PLANES;
+#pragma unroll
+                for (int blk = 0; blk < C::NB; ++blk) {
+                    tma_load_4d(sb + blk * SUB_BYTES, &map_g_hi, &full_bar[stage], nb * BLOCK_N + blk * 64, w0, h0, n);
+                    if (SPLIT)
+                        tma_load_4d(sb + C::B_BYTES + blk * SUB_BYTES, &map_g_lo, &full_bar[stage],
+                                    nb * BLOCK_N + blk * 64, w0, h0, n);
+                }
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t first = 1;
+            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                const uint32_t b_hi = a_hi + C::A_BYTES * C::PLANES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t da_hi = make_smem_desc(a_hi + k * 2048, SUB_BYTES, 1024, kSwizzle128);
+                    const uint64_t db_hi = make_smem_desc(b_hi + k * 2048, SUB_BYTES, 1024, kSwizzle128);
+                    umma_f16(tmem_base, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
+                    if (SPLIT) {
+                        const uint64_t da_lo = make_smem_desc(a_hi + C::A_BYTES + k * 2048, SUB_BYTES, 1024, kSwizzle128);
+                        const uint64_t db_lo = make_smem_desc(b_hi + C::B_BYTES + k * 2048, SUB_BYTES, 1024, kSwizzle128);
+                        umma_f16(tmem_base, da_lo, db_hi, idesc, 1u);
+                        umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
+                    }
+                }
+                first = 0;
+                umma_commit(&empty_bar[stage]);
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(done_bar);
+        }
+    } else if (pt_end > pt_begin) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;           // M row: sub-tile = row / 64, ci = row % 64
+        const int sub = row >> 6;
+        const int rg = sub == 0 ? rg0 : rg1;
+        const bool live = (sub == 0) || (2 * mb + 1 < p.R);
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        float* dst = p.ws + (static_cast<size_t>(rg) * 64 + (row & 63)) * p.Cout_p + nb * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + c + (static_cast<uint32_t>(q * 32) << 16), v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dst + c + j),
+                              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                          __uint_as_float(v[j + 3])));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS < 32 ? 32 : C::TMEM_COLS);
+    }
+}
+
+// ws[(tap*cchunks + cb)*64 + cil][co]  ->  dw[co][ci][r][s]
+__global__ void wgrad_scatter_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int Cin_p,
+                                     int Cout_p, int KH, int KW, int accumulate) {
+    const long long total = 1LL * Cout * Cin * KH * KW;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        long long t = i;
+        const int s = static_cast<int>(t % KW); t /= KW;
+        const int r = static_cast<int>(t % KH); t /= KH;
+        const int ci = static_cast<int>(t % Cin);
+        const int co = static_cast<int>(t / Cin);
+        const int tap = r * KW + s;
+        const float v = ws[(static_cast<size_t>(tap) * Cin_p + ci) * Cout_p + co];
+        dw[i] = accumulate ? dw[i] + v : v;
+    }
+}
+
+__global__ void channel_sum_kernel2(SplitCPtr v, int ld, long long npix, int C, float* out, int accumulate) {
+    // grid.x = channel groups of 32, grid.y = pixel slices; partial sums combined with float atomics after
+    // an in-block double reduction.  `out` must be pre-zeroed when accumulate == 0 (done by the wrapper).
+    __shared__ double red[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int py = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (c < C)
+        for (long long p = blockIdx.y * 8LL + py; p < npix; p += 8LL * gridDim.y)
+            acc += load_split(v, static_cast<size_t>(p) * ld + c);
+    red[py][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (py == 0 && c < C) {
+        double t = 0.0;
+        for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+        atomicAdd(out + c, static_cast<float>(t));
+    }
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
+    return stride == 1 && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH <= 9 && KW <= 9;
+}
+
+size_t wgrad_tc_workspace(int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int pad) {
+    (void)N; (void)H; (void)W; (void)pad;
+    return sizeof(float) * static_cast<size_t>(KH) * KW * Cin_p * Cout_p;
+}
+
+int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
+                      cudaStream_t stream) {
+    if (!accumulate) FCD_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, stream));
+    int gy = static_cast<int>(npix / 2048);
+    if (gy < 1) gy = 1;
+    if (gy > 1024) gy = 1024;
+    SplitCPtr v{(const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo};
+    channel_sum_kernel2<<<dim3((C + 31) / 32, gy), 256, 0, stream>>>(v, ld, npix, C, out, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mgh, const CUtensorMap& mgl,
+                        const WgradParams& p, cudaStream_t stream) {
+    using C = WCfg<BLOCK_N, SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FCD_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const unsigned grid = static_cast<unsigned>(p.m_blocks) * p.n_blocks * p.ksplit;
+    wgrad_tc_kernel<BLOCK_N, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(mxh, mxl, mgh, mgl, p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz_hi, const void* dz_lo, int dz_ld,
+                    float* dw, int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH, int KW, int pad,
+                    int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
+    const size_t need = wgrad_tc_workspace(N, H, W, Cin_p, Cout_p, KH, KW, pad);
+    FCD_CHECK_ARG(workspace && workspace_bytes >= need, "conv2d_wgrad_tc: workspace too small (%zu < %zu)",
+                  workspace_bytes, need);
+    FCD_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0, "conv2d_wgrad_tc: pitches must be multiples of 8");
+    const bool split = x_lo && dz_lo;
+    const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
+    WgradParams p;
+    p.ws = static_cast<float*>(workspace);
+    p.N = N; p.OH = OH; p.OW = OW;
+    p.Cin_p = Cin_p; p.Cout_p = Cout_p; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.cchunks = Cin_p / 64;
+    p.R = KH * KW * p.cchunks;
+    p.m_blocks = (p.R + 1) / 2;
+    p.n_blocks = Cout_p / block_n;
+    p.tiles_h = ceil_div(OH, PT_H);
+    p.tiles_w = ceil_div(OW, PT_W);
+    p.total_pt = 1LL * N * p.tiles_h * p.tiles_w;
+    const long long mn = 1LL * p.m_blocks * p.n_blocks;
+    long long ks = (2LL * sm_count() + mn - 1) / mn;
+    if (ks < 1) ks = 1;
+    if (ks > p.total_pt) ks = p.total_pt;
+    p.pt_per_split = (p.total_pt + ks - 1) / ks;
+    p.ksplit = static_cast<int>((p.total_pt + p.pt_per_split - 1) / p.pt_per_split);
+
+    CUtensorMap mxh, mxl, mgh, mgl;
+    int rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H))) return rc;
+    if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H))) return rc;
+    if (split) {
+        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H))) return rc;
+        if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H))) return rc;
+    } else {
+        mxl = mxh;
+        mgl = mgh;
+    }
+    FCD_CUDA_OK(cudaMemsetAsync(workspace, 0, need, stream));
+    if (block_n == 128)
+        rc = split ? launch_wgrad<128, true>(mxh, mxl, mgh, mgl, p, stream)
+                   : launch_wgrad<128, false>(mxh, mxl, mgh, mgl, p, stream);
+    else
+        rc = split ? launch_wgrad<64, true>(mxh, mxl, mgh, mgl, p, stream)
+                   : launch_wgrad<64, false>(mxh, mxl, mgh, mgl, p, stream);
+    if (rc) return rc;
+    const long long total = 1LL * Cout * Cin * KH * KW;
+    const int blocks = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    wgrad_scatter_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, Cin, Cout, Cin_p, Cout_p, KH, KW, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+}  // namespace fcd
