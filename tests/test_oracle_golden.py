@@ -1,0 +1,139 @@
+"""Pins the CPU oracle port (oracle/fcd_oracle.py) against golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py).  CPU only; tolerance 2e-5 relative (same torch ops, different call structure)."""
+import pytest
+import torch
+
+from oracle import fcd_oracle as O
+from tests._util import check_grad_summary, load_golden, rel_err
+
+TOL = 2e-5
+
+
+def _grads(sd):
+    return {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad}
+
+
+@pytest.mark.parametrize("name", ["g13_train.pt", "g4_eval.pt"])
+def test_generator(name):
+    f = load_golden(name)
+    sd = O.clone_sd(O.make_state_dict(O.generator_spec(f["C"]), f["seed"]), requires_grad=True)
+    x = f["x"].clone().requires_grad_(True)
+    y = O.generator(sd, x, train=f["train"])
+    assert rel_err(y, f["y"]) < TOL
+    (y * f["r"]).sum().backward()
+    assert rel_err(x.grad, f["dx"]) < 1e-4
+    check_grad_summary(_grads(sd), f["grads"], 2e-4, what=name)
+    for k, v in f["running"].items():
+        assert rel_err(sd[k].float(), v.float()) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["s13_bilinear_even.pt", "s4_bilinear_odd.pt", "s4_convT_odd.pt", "s4_bilinear_eval.pt"])
+def test_segmentor(name):
+    f = load_golden(name)
+    sd = O.clone_sd(O.make_state_dict(O.segmentor_spec(f["C"], 1, f["bilinear"]), f["seed"]), requires_grad=True)
+    x = f["x"].clone().requires_grad_(True)
+    y = f["y"].clone().requires_grad_(True)
+    cmap = O.segmentor(sd, x, y, bilinear=f["bilinear"], train=f["train"])
+    assert rel_err(cmap, f["cmap"]) < TOL
+    (cmap * f["r"]).sum().backward()
+    assert rel_err(x.grad, f["dx"]) < 2e-4 and rel_err(y.grad, f["dy"]) < 2e-4
+    check_grad_summary(_grads(sd), f["grads"], 5e-4, what=name)
+    for k, v in f["running"].items():
+        assert rel_err(sd[k].float(), v.float()) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["d13.pt", "d3_odd.pt"])
+def test_discriminator(name):
+    f = load_golden(name)
+    sd = O.clone_sd(O.make_state_dict(O.discriminator_spec(f["C"]), f["seed"]), requires_grad=True)
+    x = f["x"].clone().requires_grad_(True)
+    y = f["y"].clone().requires_grad_(True)
+    out = O.discriminator(sd, x, y, train=True)
+    assert rel_err(out, f["out"]) < TOL
+    (out * f["r"]).sum().backward()
+    assert rel_err(x.grad, f["dx"]) < 2e-4 and rel_err(y.grad, f["dy"]) < 2e-4
+    check_grad_summary(_grads(sd), f["grads"], 5e-4, what=name)
+    for k, v in f["running"].items():
+        assert rel_err(sd[k].float(), v.float()) < TOL, k
+
+
+def test_losses():
+    f = load_golden("losses.pt")
+    t = f["t"]
+    g = f["g"].clone().requires_grad_(True)
+    cmap = f["cmap"].clone().requires_grad_(True)
+    gl, l1, sl = O.cnet_loss(t, g, cmap)
+    for got, ref in zip((gl, l1, sl), f["cnet"]):
+        assert abs(got.item() - ref) <= TOL * max(abs(ref), 1e-3)
+    (gl + 0.65 * l1 + 0.7 * sl).backward()
+    assert rel_err(g.grad, f["cnet_dg"]) < 1e-4 and rel_err(cmap.grad, f["cnet_dcmap"]) < 1e-4
+
+    g2 = f["g"].clone().requires_grad_(True)
+    cmap2 = f["cmap2"].clone().requires_grad_(True)
+    gl2, sl2 = O.cgenerator_loss(t, g2, cmap2)
+    for got, ref in zip((gl2, sl2), f["cgen"]):
+        assert abs(got.item() - ref) <= TOL * max(abs(ref), 1e-3)
+    (gl2 + 0.3 * sl2).backward()
+    assert rel_err(g2.grad, f["cgen_dg"]) < 1e-4 and rel_err(cmap2.grad, f["cgen_dcmap"]) < 1e-4
+
+    cm3 = f["cmap"].clone().requires_grad_(True)
+    r1 = O.region_loss(cm3, f["region"], "l1")
+    r2 = O.region_loss(cm3, 1 - f["region"], "mse")
+    assert abs(r1.item() - f["region_l1"]) < TOL and abs(r2.item() - f["region_mse"]) < TOL
+    (0.02 * r1 + 2 * r2).backward()
+    assert rel_err(cm3.grad, f["region_dcmap"]) < 1e-4
+
+
+def test_ssim_family():
+    f = load_golden("losses.pt")
+    X, Y = f["X"], f["Y"]
+    assert abs(O.ssim(X, Y, data_range=1.0).item() - f["ssim"]) < TOL
+    assert rel_err(O.ssim(X, Y, data_range=1.0, size_average=False, nonnegative_ssim=True), f["ssim_nsa"]) < TOL
+    assert abs(O.ms_ssim(X, Y, data_range=1.0).item() - f["msssim"]) < TOL
+    assert rel_err(O.ms_ssim(X, Y, data_range=1.0, size_average=False), f["msssim_nsa"]) < TOL
+    assert abs(O.ms_ssim(X, 1 - X, data_range=1.0).item() - f["msssim_anti"]) < TOL
+    with pytest.raises(ValueError):
+        O.ms_ssim(X, Y[:, :2], data_range=1.0)
+    with pytest.raises(AssertionError):
+        O.ms_ssim(X[..., :160, :160], Y[..., :160, :160], data_range=1.0)
+
+
+def test_step_usss():
+    f = load_golden("step_usss.pt")
+    C = f["C"]
+    sdG = O.clone_sd(O.make_state_dict(O.generator_spec(C), 11), requires_grad=True)
+    sdS = O.clone_sd(O.make_state_dict(O.segmentor_spec(C, 1, True), 12), requires_grad=True)
+    loss, net_loss, cmap, parts = O.usss_joint_losses(sdG, sdS, f["x"], f["y"], f["ssim_w"], f["l1_w"])
+    for got, ref in zip(parts, f["losses"]):
+        assert abs(got.item() - ref) <= 5e-5 * max(abs(ref), 1e-3)
+    assert rel_err(cmap, f["cmap"]) < 5e-5
+    # Demo_USSS.py:327-338: G accumulates d(Loss) + d(NetLoss); S only d(NetLoss)
+    loss.backward(retain_graph=True)
+    for k, v in sdS.items():
+        if v.is_floating_point() and v.grad is not None:
+            v.grad = None
+    net_loss.backward()
+    check_grad_summary(_grads(sdG), f["gradsG"], 2e-3, what="usss G")
+    check_grad_summary(_grads(sdS), f["gradsS"], 2e-3, what="usss S")
+
+
+def test_step_rsss():
+    f = load_golden("step_rsss.pt")
+    C = f["C"]
+    sdG = O.clone_sd(O.make_state_dict(O.generator_spec(C), 11), requires_grad=True)
+    sdS = O.clone_sd(O.make_state_dict(O.segmentor_spec(C, 1, True), 12), requires_grad=True)
+    sdD = O.clone_sd(O.make_state_dict(O.discriminator_spec(C), 13), requires_grad=True)
+    x, y, region = f["x"], f["y"], f["region"]
+    d_loss, cmap, x_mask, y_mask = O.rsss_d_loss(sdS, sdD, x, y, region)
+    assert abs(d_loss.item() - f["d_loss"]) < 5e-5
+    assert rel_err(cmap, f["cmap"]) < 5e-5
+    d_loss.backward(retain_graph=True)
+    check_grad_summary(_grads(sdD), f["gradsD"], 2e-3, what="rsss D")
+    for sd in (sdS,):
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+    s_loss = O.rsss_s_loss(sdG, sdD, x, y, region, cmap, x_mask, y_mask)
+    assert abs(s_loss.item() - f["s_loss"]) < 5e-5 * max(1.0, abs(f["s_loss"]))
+    s_loss.backward()
+    check_grad_summary(_grads(sdS), f["gradsS"], 2e-3, what="rsss S")
