@@ -1,3 +1,14 @@
 """fcd-gan-pytorch_b200 — B200-native hot path of FCD-GAN (networks + loss stack) behind the reference's
-nn.Module call surface.  Import as `fcdgan_b200`."""
+nn.Module call surface.  Import as `fcdgan_b200`.
+
+    from fcdgan_b200 import Generator, Segmentor, Discriminator_SRGAN_simple      # Module.py
+    from fcdgan_b200 import CNetLoss, CGeneratorLoss, region_loss, MS_SSIM, SSIM  # Loss.py / ssim.py
+
+Everything numerical runs in hand-written sm_100a CUDA (libfcd_b200.so, C ABI in include/fcd_b200.h); there is
+no CPU fallback — constructing modules works anywhere, calling them needs a B200 and the built library.
+"""
 __version__ = "0.1.0"
+
+from .engine import get_precision, set_precision  # noqa: F401
+from .modules import (DoubleConv, Discriminator_SRGAN_simple, Down, Generator, OutConv, ResidualBlock,  # noqa: F401
+                      Segmentor, Up)

@@ -1,5 +1,8 @@
 """ctypes binding of libfcd_b200.so (the C ABI declared in include/fcd_b200.h).
 
+The argument/return types of every entry point are PARSED FROM THE HEADER, so the header is the single
+source of truth for the ABI (tests/test_abi.py checks that the library exports every declared symbol).
+
 The product path has no CPU or library fallback: if the shared library is missing or a call returns a
 non-zero status, a RuntimeError is raised (`FcdError`).
 """
@@ -7,31 +10,54 @@ from __future__ import annotations
 
 import ctypes
 import os
+import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libfcd_b200.so")
+HEADER = os.path.join(ROOT, "include", "fcd_b200.h")
 
 
 class FcdError(RuntimeError):
     pass
 
 
-_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double,
-      "z": ctypes.c_size_t, "l": ctypes.c_longlong}
+def _ctype(decl: str):
+    decl = decl.strip()
+    if "*" in decl:
+        return ctypes.c_char_p if decl.replace(" ", "") == "constchar*" else ctypes.c_void_p
+    base = re.sub(r"\bconst\b", "", decl).split()
+    # drop the parameter name (last identifier) when a type is present
+    words = base[:-1] if len(base) > 1 and base[-1] not in ("int", "float", "double", "size_t", "long") else base
+    t = " ".join(words)
+    return {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
+            "long long": ctypes.c_longlong, "void": None}[t]
 
-# name -> (argument codes, return code); 'p' pointer, 'i' int, 'f' float, 'd' double, 'z' size_t, 'l' long long.
-SIGNATURES = {
-    "fcd_version": ("", "i"),
-    "fcd_conv2d_tc_supported": ("iiiii", "i"),
-    "fcd_pack_conv_weight": ("piiiiiiippp", "i"),
-    "fcd_conv2d_fwd": ("ppipppp" + "i" * 10 + "ppip", "i"),
-    "fcd_conv2d_dgrad_strided": ("ppipppi" + "i" * 9 + "p", "i"),
-    "fcd_conv2d_wgrad_workspace": ("i" * 10, "z"),
-    "fcd_conv2d_wgrad": ("ppippipp" + "i" * 12 + "pzip", "i"),
-    "fcd_debug_umma_probe": ("ppp" + "i" * 13 + "p", "i"),
-}
+
+def parse_header(path: str = HEADER):
+    """-> {name: (restype, [argtypes])} for every `fcd_*` prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith("#"))
+    out = {}
+    for m in re.finditer(r"(const\s+char\s*\*|size_t|int)\s+(fcd_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else ctypes.c_int)
+        argtypes = [] if args in ("", "void") else [_ctype(a) for a in args.split(",")]
+        out[name] = (restype, argtypes)
+    return out
+
 
 _lib = None
+_sigs = None
+
+
+def signatures():
+    global _sigs
+    if _sigs is None:
+        _sigs = parse_header()
+    return _sigs
 
 
 def load():
@@ -44,22 +70,12 @@ def load():
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the fcdgan_b200 hot path)")
     lib = ctypes.CDLL(LIB_PATH)
-    lib.fcd_last_error.restype = ctypes.c_char_p
-    lib.fcd_last_error.argtypes = []
-    for name, (args, ret) in SIGNATURES.items():
-        fn = getattr(lib, name)
-        fn.argtypes = [_T[a] for a in args]
-        fn.restype = _T[ret]
+    for name, (restype, argtypes) in signatures().items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = restype
     _lib = lib
     return lib
-
-
-def register(name: str, args: str, ret: str = "i"):
-    SIGNATURES[name] = (args, ret)
-    if _lib is not None:
-        fn = getattr(_lib, name)
-        fn.argtypes = [_T[a] for a in args]
-        fn.restype = _T[ret]
 
 
 def call(name: str, *args):

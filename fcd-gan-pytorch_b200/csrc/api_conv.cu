@@ -27,12 +27,12 @@ int sm_count() {
 
 // implemented in conv_tc.cu / conv_simt.cu / wgrad_tc.cu
 bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);
-int conv2d_fwd_tc(const void*, const void*, int, const void*, const void*, const float*, float*, int, int, int, int,
-                  int, int, int, int, int, double*, double*, cudaStream_t);
-int conv2d_fwd_simt(const void*, const void*, int, const void*, const void*, const float*, float*, int, int, int, int,
-                    int, int, int, int, int, int, double*, double*, cudaStream_t);
-int conv2d_dgrad_strided_simt(const void*, const void*, int, const void*, const void*, float*, int, int, int, int, int,
-                              int, int, int, int, int, cudaStream_t);
+int conv2d_fwd_tc(const void*, const void*, int, const void*, const void*, const float*, const float*, int, float*, int,
+                  int, int, int, int, int, int, int, int, double*, double*, cudaStream_t);
+int conv2d_fwd_simt(const void*, const void*, int, const void*, const void*, const float*, const float*, int, float*,
+                    int, int, int, int, int, int, int, int, int, int, double*, double*, cudaStream_t);
+int conv2d_dgrad_strided_simt(const void*, const void*, int, const void*, const void*, const float*, int, float*, int,
+                              int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv2d_wgrad_simt(const void*, const void*, int, const void*, const void*, int, float*, float*, int, int, int, int,
                       int, int, int, int, int, int, int, int, cudaStream_t);
 int pack_conv_weight(const float*, int, int, int, int, int, int, int, void*, void*, cudaStream_t);
@@ -64,7 +64,7 @@ int fcd_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW,
 }
 
 int fcd_conv2d_fwd(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
-                   const float* bias, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
+                   const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
                    int stride, int pad, double* stat_sum, double* stat_sqsum, int engine, void* stream) {
     FCD_CHECK_ARG(x_hi && w_hi && z, "fcd_conv2d_fwd: null pointer");
     FCD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin_p > 0 && Cout_p > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0,
@@ -77,17 +77,17 @@ int fcd_conv2d_fwd(const void* x_hi, const void* x_lo, int x_ld, const void* w_h
         return FCD_ERR_UNSUPPORTED;
     }
     if (engine == FCD_ENGINE_TC || (engine == FCD_ENGINE_AUTO && tc_ok))
-        return conv2d_fwd_tc(x_hi, x_lo, x_ld, w_hi, w_lo, bias, z, z_ld, N, H, W, Cin_p, Cout_p, KH, KW, pad, stat_sum,
-                             stat_sqsum, as_stream(stream));
-    return conv2d_fwd_simt(x_hi, x_lo, x_ld, w_hi, w_lo, bias, z, z_ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad,
-                           stat_sum, stat_sqsum, as_stream(stream));
+        return conv2d_fwd_tc(x_hi, x_lo, x_ld, w_hi, w_lo, bias, addend, addend_ld, z, z_ld, N, H, W, Cin_p, Cout_p, KH,
+                             KW, pad, stat_sum, stat_sqsum, as_stream(stream));
+    return conv2d_fwd_simt(x_hi, x_lo, x_ld, w_hi, w_lo, bias, addend, addend_ld, z, z_ld, N, H, W, Cin_p, Cout_p, KH,
+                           KW, stride, pad, stat_sum, stat_sqsum, as_stream(stream));
 }
 
 int fcd_conv2d_dgrad_strided(const void* dz_hi, const void* dz_lo, int dz_ld, const void* w_hi, const void* w_lo,
-                             float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
+                             const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
                              int stride, int pad, void* stream) {
     FCD_CHECK_ARG(dz_hi && w_hi && dx, "fcd_conv2d_dgrad_strided: null pointer");
-    return conv2d_dgrad_strided_simt(dz_hi, dz_lo, dz_ld, w_hi, w_lo, dx, dx_ld, N, H, W, Cin_p, Cout_p, KH, KW, stride,
+    return conv2d_dgrad_strided_simt(dz_hi, dz_lo, dz_ld, w_hi, w_lo, addend, addend_ld, dx, dx_ld, N, H, W, Cin_p, Cout_p, KH, KW, stride,
                                      pad, as_stream(stream));
 }
 

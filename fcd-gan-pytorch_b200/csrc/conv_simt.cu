@@ -42,8 +42,8 @@ struct ConvDims {
 //         packing [tap][Cout_p(K side)][Cin_p(columns)], i.e. B is read k-major-by-row.
 template <int MODE>
 __global__ void __launch_bounds__(NT)
-conv_simt_kernel(SplitCPtr x, int x_ld, SplitCPtr w, const float* __restrict__ bias, float* __restrict__ z, int z_ld,
-                 ConvDims d, double* stat_sum, double* stat_sqsum) {
+conv_simt_kernel(SplitCPtr x, int x_ld, SplitCPtr w, const float* __restrict__ bias, const float* __restrict__ addend,
+                 int addend_ld, float* __restrict__ z, int z_ld, ConvDims d, double* stat_sum, double* stat_sqsum) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
 
@@ -135,7 +135,12 @@ conv_simt_kernel(SplitCPtr x, int x_ld, SplitCPtr w, const float* __restrict__ b
             const int oh = th * 8 + (prow >> 3), ow = tw * 8 + (prow & 7);
             if (oh < d.OH && ow < d.OW) {
                 float4 o = make_float4(acc[i][0] + b4[0], acc[i][1] + b4[1], acc[i][2] + b4[2], acc[i][3] + b4[3]);
-                *reinterpret_cast<float4*>(z + ((static_cast<size_t>(n) * d.OH + oh) * d.OW + ow) * z_ld + c) = o;
+                const size_t pix = (static_cast<size_t>(n) * d.OH + oh) * d.OW + ow;
+                if (addend) {
+                    const float4 a = *reinterpret_cast<const float4*>(addend + pix * addend_ld + c);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                }
+                *reinterpret_cast<float4*>(z + pix * z_ld + c) = o;
                 ssum[0] += o.x; ssum[1] += o.y; ssum[2] += o.z; ssum[3] += o.w;
                 ssq[0] += o.x * o.x; ssq[1] += o.y * o.y; ssq[2] += o.z * o.z; ssq[3] += o.w * o.w;
             }
@@ -269,8 +274,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 }  // namespace
 
 int conv2d_fwd_simt(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
-                    const float* bias, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
-                    int stride, int pad, double* stat_sum, double* stat_sqsum, cudaStream_t stream) {
+                    const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W,
+                    int Cin_p, int Cout_p, int KH, int KW, int stride, int pad, double* stat_sum, double* stat_sqsum,
+                    cudaStream_t stream) {
     ConvDims d;
     d.N = N; d.H = H; d.W = W;
     d.OH = (H + 2 * pad - KH) / stride + 1;
@@ -282,13 +288,13 @@ int conv2d_fwd_simt(const void* x_hi, const void* x_lo, int x_ld, const void* w_
     dim3 grid(N * ((d.OH + 7) / 8) * ((d.OW + 7) / 8), (Cout_p + TN - 1) / TN);
     SplitCPtr x{(const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo};
     SplitCPtr w{(const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo};
-    conv_simt_kernel<0><<<grid, NT, 0, stream>>>(x, x_ld, w, bias, z, z_ld, d, stat_sum, stat_sqsum);
+    conv_simt_kernel<0><<<grid, NT, 0, stream>>>(x, x_ld, w, bias, addend, addend_ld, z, z_ld, d, stat_sum, stat_sqsum);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
 
 int conv2d_dgrad_strided_simt(const void* dz_hi, const void* dz_lo, int dz_ld, const void* w_hi, const void* w_lo,
-                              float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
+                              const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
                               int stride, int pad, cudaStream_t stream) {
     // H, W are the INPUT (dx) dims; dz has dims OH x OW.
     ConvDims d;
@@ -304,7 +310,7 @@ int conv2d_dgrad_strided_simt(const void* dz_hi, const void* dz_lo, int dz_ld, c
     dim3 grid(N * ((H + 7) / 8) * ((W + 7) / 8), (Cin_p + TN - 1) / TN);
     SplitCPtr g{(const __nv_bfloat16*)dz_hi, (const __nv_bfloat16*)dz_lo};
     SplitCPtr w{(const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo};
-    conv_simt_kernel<1><<<grid, NT, 0, stream>>>(g, dz_ld, w, nullptr, dx, dx_ld, d, nullptr, nullptr);
+    conv_simt_kernel<1><<<grid, NT, 0, stream>>>(g, dz_ld, w, nullptr, addend, addend_ld, dx, dx_ld, d, nullptr, nullptr);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

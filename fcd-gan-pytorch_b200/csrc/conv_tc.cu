@@ -49,6 +49,8 @@ struct Cfg {
 
 struct ConvTcParams {
     const float* bias;
+    const float* addend;  // optional fp32 NHWC tensor added in the epilogue (gradient accumulation / residual)
+    int addend_ld;
     float* z;
     double* stat_sum;
     double* stat_sqsum;
@@ -205,8 +207,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
             const int n = static_cast<int>(t / p.tiles_h);
             const int oh = th * TILE_H + lh, ow = tw * TILE_W + lw;
             const bool valid = (oh < p.OH) && (ow < p.OW);
-            float* zrow = p.z + (static_cast<size_t>(n) * p.OH * p.OW + static_cast<size_t>(oh) * p.OW + ow) * p.z_ld +
-                          nblk * BLOCK_N;
+            const size_t pix = static_cast<size_t>(n) * p.OH * p.OW + static_cast<size_t>(oh) * p.OW + ow;
+            float* zrow = p.z + pix * p.z_ld + nblk * BLOCK_N;
+            const float* arow = p.addend ? p.addend + pix * p.addend_ld + nblk * BLOCK_N : nullptr;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -221,6 +224,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     if (p.bias) f[j] += __ldg(p.bias + nblk * BLOCK_N + c + j);
                 }
                 if (valid) {
+                    if (arow) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 a = *reinterpret_cast<const float4*>(arow + c + j);
+                            f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(zrow + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -349,11 +359,12 @@ static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const 
 }
 
 int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
-                  const float* bias, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
-                  int pad, double* stat_sum, double* stat_sqsum, cudaStream_t stream) {
+                  const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W,
+                  int Cin_p, int Cout_p, int KH, int KW, int pad, double* stat_sum, double* stat_sqsum,
+                  cudaStream_t stream) {
     const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
     FCD_CHECK_ARG(OH > 0 && OW > 0, "conv2d_fwd_tc: empty output");
-    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0, "conv2d_fwd_tc: pitches must keep 16-byte alignment");
+    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0 && addend_ld % 4 == 0, "conv2d_fwd_tc: pitches must keep 16-byte alignment");
     const bool split = (x_lo != nullptr) && (w_lo != nullptr);
     const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
 
@@ -370,6 +381,8 @@ int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi
     }
     ConvTcParams p;
     p.bias = bias;
+    p.addend = addend;
+    p.addend_ld = addend_ld;
     p.z = z;
     p.stat_sum = stat_sum;
     p.stat_sqsum = stat_sqsum;

@@ -1,0 +1,779 @@
+// elementwise.cu — the HBM-bound glue between convolutions: staging NCHW<->NHWC, BatchNorm
+// finalize / apply+activation (forward and backward), 2x2 max-pool, bilinear x2 up-sampling, the
+// pixel-shuffle halves of ConvTranspose2d(k2,s2).  All kernels stream 8 channels (16 B of bf16 per
+// plane / 32 B of fp32) per thread with the channel index fastest, so warps touch whole 128-byte lines.
+//
+// Reference call sites: nn.BatchNorm2d Module.py:27,30,156,178,181,200,204,208; ReLU/PReLU/LeakyReLU
+// Module.py:28,31,147,179,197-209; MaxPool2d Module.py:44; Upsample(bilinear, align_corners=True)
+// Module.py:60; F.pad + torch.cat Module.py:73-78; ConvTranspose2d Module.py:63.
+#include "fcd_common.cuh"
+
+namespace fcd {
+namespace {
+
+constexpr int NT = 256;
+
+struct F8 {
+    float v[8];
+};
+__device__ __forceinline__ F8 ld_f32x8(const float* p) {
+    F8 r;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_f32x8(float* p, const F8& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
+    F8 r;
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ F8 ld_split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off) {
+    F8 r = ld_bf16x8(hi + off);
+    if (lo) {
+        const F8 l = ld_bf16x8(lo + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] += l.v[i];
+    }
+    return r;
+}
+__device__ __forceinline__ void st_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const F8& r) {
+    uint4 uh, ul;
+    __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&uh);
+    __nv_bfloat162* pl = reinterpret_cast<__nv_bfloat162*>(&ul);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(r.v[2 * i]), h1 = __float2bfloat16_rn(r.v[2 * i + 1]);
+        ph[i] = __halves2bfloat162(h0, h1);
+        pl[i] = __halves2bfloat162(__float2bfloat16_rn(r.v[2 * i] - __bfloat162float(h0)),
+                                   __float2bfloat16_rn(r.v[2 * i + 1] - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(hi + off) = uh;
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = ul;
+}
+
+// ---------------------------------------------------------------------------------------------
+// staging
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 (N,C,H,W) -> split NHWC with Cp >= C channels (zero padded).  Optional per-pixel factor
+// (1 - mask[n,0,h,w]) fuses the soft masking x*(1-cmap) of Demo_RSSS.py:290-291.
+__global__ void stage_kernel(const float* __restrict__ src, const float* __restrict__ mask, int C, int Cp, long long HW,
+                             long long npix, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long n = pix / HW, p = pix - n * HW;
+    const float f = mask ? 1.f - mask[pix] : 1.f;
+    const float* s = src + n * C * HW + p;
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.v[j] = (c0 + j < C) ? s[(c0 + j) * HW] * f : 0.f;
+        st_split8(hi, lo, static_cast<size_t>(pix) * ld + c0, r);
+    }
+}
+
+// fp32 NHWC (pitch ld) -> NCHW fp32 (N,C,H,W); `accumulate` adds into dst.
+__global__ void unstage_kernel(const float* __restrict__ src, int ld, int C, long long HW, long long npix,
+                               float* __restrict__ dst, int accumulate) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long n = pix / HW, p = pix - n * HW;
+    const float* s = src + static_cast<size_t>(pix) * ld;
+    float* d = dst + n * C * HW + p;
+    for (int c = 0; c < C; ++c) {
+        const float v = s[c];
+        d[c * HW] = accumulate ? d[c * HW] + v : v;
+    }
+}
+
+// split NHWC (pitch ld) -> NCHW fp32 (block boundary of the stand-alone DoubleConv/Down/Up/ResidualBlock modules)
+__global__ void unstage_split_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int C, long long HW,
+                                     long long npix, float* __restrict__ dst) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long n = pix / HW, p = pix - n * HW;
+    float* d = dst + n * C * HW + p;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+        const F8 v = ld_split8(hi, lo, static_cast<size_t>(pix) * ld + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < C) d[(c0 + j) * HW] = v.v[j];
+    }
+}
+
+// NCHW fp32 -> fp32 NHWC (pitch ld, Cp channels, zero padded): an incoming boundary gradient
+__global__ void stage_f32_kernel(const float* __restrict__ src, int C, int Cp, long long HW, long long npix,
+                                 float* __restrict__ dst, int ld) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long n = pix / HW, p = pix - n * HW;
+    const float* s = src + n * C * HW + p;
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.v[j] = (c0 + j < C) ? s[(c0 + j) * HW] : 0.f;
+        st_f32x8(dst + static_cast<size_t>(pix) * ld + c0, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm statistics -> per-channel affine
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const float* __restrict__ z, int ld, long long npix, int Cp, double* sum, double* sq) {
+    // blockDim = 256; channel group (8 ch) = tid % cg; pixel lane = tid / cg
+    const int cg = Cp / 8;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = blockIdx.x * 1LL * lanes + lane; p < npix; p += 1LL * gridDim.x * lanes) {
+        const F8 v = ld_f32x8(z + static_cast<size_t>(p) * ld + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] += v.v[j];
+            b[j] = fmaf(v.v[j], v.v[j], b[j]);
+        }
+    }
+    __shared__ float red[NT * 16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x * 16 + j] = a[j];
+        red[threadIdx.x * 16 + 8 + j] = b[j];
+    }
+    __syncthreads();
+    // thread t < cg*16 reduces column (group t/16, slot t%16) over the pixel lanes
+    for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
+        const int gg = t / 16, slot = t % 16;
+        double acc = 0.0;
+        for (int l = 0; l < lanes; ++l) acc += red[(l * cg + gg) * 16 + slot];
+        if (slot < 8)
+            atomicAdd(sum + gg * 8 + slot, acc);
+        else
+            atomicAdd(sq + gg * 8 + slot - 8, acc);
+    }
+}
+
+// mode: 1 = training (batch statistics, running stats updated), 0 = eval (running statistics)
+__global__ void bn_finalize_kernel(const double* sum, const double* sq, double count, const float* gamma,
+                                   const float* beta, float* running_mean, float* running_var, int C, int Cp,
+                                   float momentum, float eps, int mode, float* scale, float* shift, float* mean_out,
+                                   float* invstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    if (c >= C) {
+        scale[c] = 0.f; shift[c] = 0.f; mean_out[c] = 0.f; invstd_out[c] = 0.f;
+        return;
+    }
+    double mean, var;
+    if (mode) {
+        mean = sum[c] / count;
+        var = sq[c] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double sc = gamma[c] * invstd;
+    scale[c] = static_cast<float>(sc);
+    shift[c] = static_cast<float>(beta[c] - mean * sc);
+    mean_out[c] = static_cast<float>(mean);
+    invstd_out[c] = static_cast<float>(invstd);
+}
+
+// out = act(z*scale + shift) (+ residual), written as a split tensor and/or fp32
+__global__ void bn_act_fwd_kernel(const float* __restrict__ z, int z_ld, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act, const float* slope_ptr, float slope_const,
+                                  const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo, int res_ld,
+                                  __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld, long long npix, int Cp) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const long long pix = idx / cg;
+    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    const float slope = slope_ptr ? *slope_ptr : slope_const;
+    F8 v = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
+    if (scale) {
+        const F8 sc = ld_f32x8(scale + c0), sh = ld_f32x8(shift + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = act_fwd(act, v.v[j], slope);
+    if (res_hi) {
+        const F8 r = ld_split8(res_hi, res_lo, static_cast<size_t>(pix) * res_ld + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
+    }
+    st_split8(out_hi, out_lo, static_cast<size_t>(pix) * out_ld + c0, v);
+}
+
+// s1[c] += sum dy, s2[c] += sum dy * xhat, dslope += sum da * u * [u <= 0]   (dy = da * act'(u))
+__global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ da, int da_ld, const float* __restrict__ z, int z_ld,
+                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                         const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                         const float* slope_ptr, float slope_const, long long npix, int Cp, double* s1,
+                                         double* s2, double* dslope) {
+    const int cg = Cp / 8;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
+    const float slope = slope_ptr ? *slope_ptr : slope_const;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ds = 0.f;
+    F8 sc, sh, mu, is;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc.v[j] = 1.f; sh.v[j] = 0.f; mu.v[j] = 0.f; is.v[j] = 1.f; }
+    if (scale) {
+        sc = ld_f32x8(scale + g * 8); sh = ld_f32x8(shift + g * 8);
+        mu = ld_f32x8(mean + g * 8); is = ld_f32x8(invstd + g * 8);
+    }
+    for (long long p = blockIdx.x * 1LL * lanes + lane; p < npix; p += 1LL * gridDim.x * lanes) {
+        const F8 zz = ld_f32x8(z + static_cast<size_t>(p) * z_ld + g * 8);
+        const F8 dd = ld_f32x8(da + static_cast<size_t>(p) * da_ld + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = fmaf(zz.v[j], sc.v[j], sh.v[j]);
+            const float dy = dd.v[j] * act_grad(act, u, slope);
+            a[j] += dy;
+            b[j] = fmaf(dy, (zz.v[j] - mu.v[j]) * is.v[j], b[j]);
+            if (act == FCD_ACT_PRELU && !(u > 0.f)) ds = fmaf(dd.v[j], u, ds);
+        }
+    }
+    __shared__ float red[NT * 16];
+    __shared__ float red_ds[NT / 32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x * 16 + j] = a[j];
+        red[threadIdx.x * 16 + 8 + j] = b[j];
+    }
+    if (dslope) {
+        ds = warp_sum(ds);
+        if ((threadIdx.x & 31) == 0) red_ds[threadIdx.x >> 5] = ds;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
+        const int gg = t / 16, slot = t % 16;
+        double acc = 0.0;
+        for (int l = 0; l < lanes; ++l) acc += red[(l * cg + gg) * 16 + slot];
+        if (slot < 8)
+            atomicAdd(s1 + gg * 8 + slot, acc);
+        else
+            atomicAdd(s2 + gg * 8 + slot - 8, acc);
+    }
+    if (dslope && threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NT / 32; ++w) t += red_ds[w];
+        atomicAdd(dslope, t);
+    }
+}
+
+// per-channel backward coefficients + parameter gradients:
+//   training: c1 = s1/count, c2 = s2/count;  eval: c1 = c2 = 0.   dgamma (+)= s2, dbeta (+)= s1, dslope (+)= ds.
+__global__ void bn_bwd_finalize_kernel(const double* s1, const double* s2, double count, int train, int C, int Cp,
+                                       float* c1, float* c2, float* dgamma, float* dbeta, int accumulate,
+                                       const double* ds, float* dslope) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && dslope) *dslope = (accumulate ? *dslope : 0.f) + static_cast<float>(*ds);
+    if (c >= Cp) return;
+    c1[c] = (train && c < C) ? static_cast<float>(s1[c] / count) : 0.f;
+    c2[c] = (train && c < C) ? static_cast<float>(s2[c] / count) : 0.f;
+    if (c < C) {
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(s2[c]);
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(s1[c]);
+    }
+}
+
+// dz = scale * (dy - c1 - xhat * c2), dy = da * act'(u);  written split (operand of dgrad / wgrad)
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ da, int da_ld, const float* __restrict__ z, int z_ld,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ c1, const float* __restrict__ c2, int act,
+                                        const float* slope_ptr, float slope_const, __nv_bfloat16* dz_hi,
+                                        __nv_bfloat16* dz_lo, int dz_ld, long long npix, int Cp) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const long long pix = idx / cg;
+    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    const float slope = slope_ptr ? *slope_ptr : slope_const;
+    const F8 dd = ld_f32x8(da + static_cast<size_t>(pix) * da_ld + c0);
+    F8 out;
+    if (scale) {
+        const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
+        const F8 sc = ld_f32x8(scale + c0), sh = ld_f32x8(shift + c0), mu = ld_f32x8(mean + c0),
+                 is = ld_f32x8(invstd + c0), k1 = ld_f32x8(c1 + c0), k2 = ld_f32x8(c2 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = fmaf(zz.v[j], sc.v[j], sh.v[j]);
+            const float dy = dd.v[j] * act_grad(act, u, slope);
+            out.v[j] = sc.v[j] * (dy - k1.v[j] - (zz.v[j] - mu.v[j]) * is.v[j] * k2.v[j]);
+        }
+    } else if (act != FCD_ACT_NONE) {
+        const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out.v[j] = dd.v[j] * act_grad(act, zz.v[j], slope);
+    } else {
+        out = dd;
+    }
+    st_split8(dz_hi, dz_lo, static_cast<size_t>(pix) * dz_ld + c0, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(2)  (floor: an odd last row / column is dropped)
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int in_ld, int N, int H, int W,
+                                   int Cp, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld) {
+    const int OH = H / 2, OW = W / 2, cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * N * OH * OW * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH);
+    const int n = static_cast<int>(t / OH);
+    const size_t base = ((static_cast<size_t>(n) * H + 2 * oh) * W + 2 * ow) * in_ld + c0;
+    F8 m = ld_split8(in_hi, in_lo, base);
+    const size_t offs[3] = {static_cast<size_t>(in_ld), static_cast<size_t>(W) * in_ld, static_cast<size_t>(W + 1) * in_ld};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const F8 v = ld_split8(in_hi, in_lo, base + offs[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m.v[j] = v.v[j] > m.v[j] ? v.v[j] : m.v[j];
+    }
+    st_split8(out_hi, out_lo, ((static_cast<size_t>(n) * OH + oh) * OW + ow) * out_ld + c0, m);
+}
+
+// d_in[h,w] (+)= d_out[h/2,w/2] iff (h,w) is the first maximum of its window (torch keeps the first index)
+__global__ void maxpool_bwd_kernel(const float* __restrict__ d_out, int dout_ld, const __nv_bfloat16* in_hi,
+                                   const __nv_bfloat16* in_lo, int in_ld, int N, int H, int W, int Cp, float* d_in,
+                                   int din_ld, int accumulate) {
+    const int OH = H / 2, OW = W / 2, cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * N * H * W * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float* dst = d_in + ((static_cast<size_t>(n) * H + h) * W + w) * din_ld + c0;
+    F8 g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+    const int oh = h / 2, ow = w / 2;
+    if (oh < OH && ow < OW) {
+        const size_t base = ((static_cast<size_t>(n) * H + 2 * oh) * W + 2 * ow) * in_ld + c0;
+        const size_t offs[4] = {0, static_cast<size_t>(in_ld), static_cast<size_t>(W) * in_ld,
+                                static_cast<size_t>(W + 1) * in_ld};
+        const int me = (h & 1) * 2 + (w & 1);
+        F8 m = ld_split8(in_hi, in_lo, base);
+        int arg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const F8 v = ld_split8(in_hi, in_lo, base + offs[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (v.v[j] > m.v[j]) {
+                    m.v[j] = v.v[j];
+                    arg[j] = k;
+                }
+        }
+        const F8 go = ld_f32x8(d_out + ((static_cast<size_t>(n) * OH + oh) * OW + ow) * dout_ld + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = (arg[j] == me) ? go.v[j] : 0.f;
+    }
+    if (accumulate) {
+        const F8 old = ld_f32x8(dst);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
+    }
+    st_f32x8(dst, g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2 up-sampling (align_corners=True) written into a (possibly larger, zero padded) destination
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_coord(int o, float ratio, int in, int& i0, int& i1, float& l1) {
+    const float f = ratio * o;  // torch: area_pixel_compute_source_index(align_corners=True)
+    i0 = static_cast<int>(f);
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = f - i0;
+}
+
+__global__ void upsample_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int in_ld, int N, int h, int w,
+                                    int Cp, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld, int H, int W,
+                                    int pad_top, int pad_left) {
+    const int cg = Cp / 8, uh = 2 * h, uw = 2 * w;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * N * H * W * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int X = static_cast<int>(t % W); t /= W;
+    const int Y = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+    const int oy = Y - pad_top, ox = X - pad_left;
+    if (oy >= 0 && oy < uh && ox >= 0 && ox < uw) {
+        const float rh = uh > 1 ? static_cast<float>(h - 1) / (uh - 1) : 0.f;
+        const float rw = uw > 1 ? static_cast<float>(w - 1) / (uw - 1) : 0.f;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_coord(oy, rh, h, y0, y1, ly);
+        src_coord(ox, rw, w, x0, x1, lx);
+        const size_t b = static_cast<size_t>(n) * h * w;
+        const F8 v00 = ld_split8(in_hi, in_lo, (b + static_cast<size_t>(y0) * w + x0) * in_ld + c0);
+        const F8 v01 = ld_split8(in_hi, in_lo, (b + static_cast<size_t>(y0) * w + x1) * in_ld + c0);
+        const F8 v10 = ld_split8(in_hi, in_lo, (b + static_cast<size_t>(y1) * w + x0) * in_ld + c0);
+        const F8 v11 = ld_split8(in_hi, in_lo, (b + static_cast<size_t>(y1) * w + x1) * in_ld + c0);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o.v[j] = hy * (hx * v00.v[j] + lx * v01.v[j]) + ly * (hx * v10.v[j] + lx * v11.v[j]);
+    }
+    st_split8(out_hi, out_lo, ((static_cast<size_t>(n) * H + Y) * W + X) * out_ld + c0, o);
+}
+
+// gather form of the backward: every source pixel sums the (<= 6x6) destination pixels that read it
+__global__ void upsample_bwd_kernel(const float* __restrict__ d_out, int dout_ld, int N, int h, int w, int Cp, int H,
+                                    int W, int pad_top, int pad_left, float* d_in, int din_ld) {
+    const int cg = Cp / 8, uh = 2 * h, uw = 2 * w;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * N * h * w * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int x = static_cast<int>(t % w); t /= w;
+    const int y = static_cast<int>(t % h);
+    const int n = static_cast<int>(t / h);
+    const float rh = uh > 1 ? static_cast<float>(h - 1) / (uh - 1) : 0.f;
+    const float rw = uw > 1 ? static_cast<float>(w - 1) / (uw - 1) : 0.f;
+    // candidate destination range: src(o) in (y-1, y+1)
+    int oy_lo = rh > 0.f ? static_cast<int>(floorf((y - 1) / rh)) - 1 : 0;
+    int oy_hi = rh > 0.f ? static_cast<int>(ceilf((y + 1) / rh)) + 1 : uh - 1;
+    int ox_lo = rw > 0.f ? static_cast<int>(floorf((x - 1) / rw)) - 1 : 0;
+    int ox_hi = rw > 0.f ? static_cast<int>(ceilf((x + 1) / rw)) + 1 : uw - 1;
+    oy_lo = max(oy_lo, 0); ox_lo = max(ox_lo, 0);
+    oy_hi = min(oy_hi, uh - 1); ox_hi = min(ox_hi, uw - 1);
+    F8 g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        int y0, y1;
+        float ly;
+        src_coord(oy, rh, h, y0, y1, ly);
+        float wy = 0.f;
+        if (y0 == y) wy += 1.f - ly;
+        if (y1 == y) wy += (y1 != y0) ? ly : ly;  // when y1 == y0 (last row) both weights land on the same pixel
+        if (y0 == y && y1 == y) wy = 1.f;
+        if (wy == 0.f) continue;
+        const int Y = oy + pad_top;
+        if (Y < 0 || Y >= H) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+            int x0, x1;
+            float lx;
+            src_coord(ox, rw, w, x0, x1, lx);
+            float wx = 0.f;
+            if (x0 == x) wx += 1.f - lx;
+            if (x1 == x) wx += lx;
+            if (x0 == x && x1 == x) wx = 1.f;
+            if (wx == 0.f) continue;
+            const int X = ox + pad_left;
+            if (X < 0 || X >= W) continue;
+            const F8 v = ld_f32x8(d_out + ((static_cast<size_t>(n) * H + Y) * W + X) * dout_ld + c0);
+            const float ww = wy * wx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.v[j] = fmaf(ww, v.v[j], g.v[j]);
+        }
+    }
+    st_f32x8(d_in + ((static_cast<size_t>(n) * h + y) * w + x) * din_ld + c0, g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose2d(k2,s2) = four 1x1 convolutions + pixel shuffle.  These two kernels are the shuffles.
+// ---------------------------------------------------------------------------------------------
+// src fp32 [4][N,h,w,Cp] (one plane per (i,j) sub-pixel)  ->  split dst slice (N,H,W) at (2y+i+pad_top, 2x+j+pad_left);
+// pixels of dst outside the 2h x 2w region are zero filled.
+__global__ void shuffle_up_kernel(const float* __restrict__ src, long long plane_stride, int src_ld, int N, int h, int w,
+                                  int Cp, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld, int H, int W,
+                                  int pad_top, int pad_left) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * N * H * W * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int X = static_cast<int>(t % W); t /= W;
+    const int Y = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+    const int oy = Y - pad_top, ox = X - pad_left;
+    if (oy >= 0 && oy < 2 * h && ox >= 0 && ox < 2 * w) {
+        const int sub = (oy & 1) * 2 + (ox & 1);
+        o = ld_f32x8(src + sub * plane_stride + ((static_cast<size_t>(n) * h + (oy >> 1)) * w + (ox >> 1)) * src_ld + c0);
+    }
+    st_split8(out_hi, out_lo, ((static_cast<size_t>(n) * H + Y) * W + X) * out_ld + c0, o);
+}
+
+// d_out fp32 (N,H,W) slice -> split [4][N,h,w,Cp] planes (the dz operand of the four 1x1 dgrad / wgrad calls)
+__global__ void shuffle_down_kernel(const float* __restrict__ d_out, int dout_ld, int N, int h, int w, int Cp, int H,
+                                    int W, int pad_top, int pad_left, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
+                                    long long plane_stride, int g_ld) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 4LL * N * h * w * cg) return;
+    long long t = idx;
+    const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
+    const int x = static_cast<int>(t % w); t /= w;
+    const int y = static_cast<int>(t % h); t /= h;
+    const int n = static_cast<int>(t % N);
+    const int sub = static_cast<int>(t / N);
+    const int Y = 2 * y + (sub >> 1) + pad_top, X = 2 * x + (sub & 1) + pad_left;
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+    if (Y >= 0 && Y < H && X >= 0 && X < W) o = ld_f32x8(d_out + ((static_cast<size_t>(n) * H + Y) * W + X) * dout_ld + c0);
+    const size_t off = sub * plane_stride + ((static_cast<size_t>(n) * h + y) * w + x) * g_ld + c0;
+    st_split8(g_hi, g_lo, off, o);
+}
+
+// fp32 NHWC -> split NHWC copy (channel slice aware); used to turn a gradient into a conv operand
+__global__ void f32_to_split_kernel(const float* __restrict__ src, int src_ld, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                    int dst_ld, long long npix, int Cp) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const long long pix = idx / cg;
+    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    st_split8(hi, lo, static_cast<size_t>(pix) * dst_ld + c0, ld_f32x8(src + static_cast<size_t>(pix) * src_ld + c0));
+}
+
+// dst += src on fp32 NHWC (pitch aware)
+__global__ void add_f32_kernel(float* __restrict__ dst, int dst_ld, const float* __restrict__ src, int src_ld,
+                               long long npix, int Cp) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const long long pix = idx / cg;
+    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    F8 a = ld_f32x8(dst + static_cast<size_t>(pix) * dst_ld + c0);
+    const F8 b = ld_f32x8(src + static_cast<size_t>(pix) * src_ld + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] += b.v[j];
+    st_f32x8(dst + static_cast<size_t>(pix) * dst_ld + c0, a);
+}
+
+inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + NT - 1) / NT); }
+
+inline int reduce_grid(long long npix, int lanes) {
+    long long want = (npix + lanes * 8 - 1) / (lanes * 8);
+    const long long cap = 8LL * sm_count();
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+}  // namespace
+}  // namespace fcd
+
+using namespace fcd;
+
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, int H, int W, void* dst_hi, void* dst_lo,
+                            int dst_ld, int Cp, void* stream) {
+    FCD_CHECK_ARG(src && dst_hi && Cp % 8 == 0 && Cp >= C && dst_ld % 8 == 0, "fcd_stage_nchw_to_split: bad arguments");
+    const long long npix = 1LL * N * H * W;
+    stage_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, mask, C, Cp, 1LL * H * W, npix, BF(dst_hi),
+                                                                  BF(dst_lo), dst_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_unstage_f32_to_nchw(const float* src, int src_ld, int N, int C, int H, int W, float* dst, int accumulate,
+                            void* stream) {
+    FCD_CHECK_ARG(src && dst, "fcd_unstage_f32_to_nchw: null pointer");
+    const long long npix = 1LL * N * H * W;
+    unstage_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, src_ld, C, 1LL * H * W, npix, dst, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_unstage_split_to_nchw(const void* src_hi, const void* src_lo, int src_ld, int N, int C, int H, int W, float* dst,
+                               void* stream) {
+    FCD_CHECK_ARG(src_hi && dst && src_ld % 8 == 0, "fcd_unstage_split_to_nchw: bad arguments");
+    const long long npix = 1LL * N * H * W;
+    unstage_split_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(CBF(src_hi), CBF(src_lo), src_ld, C, 1LL * H * W,
+                                                                          npix, dst);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_stage_nchw_to_f32(const float* src, int N, int C, int H, int W, float* dst, int dst_ld, int Cp, void* stream) {
+    FCD_CHECK_ARG(src && dst && Cp % 8 == 0 && Cp >= C && dst_ld % 4 == 0, "fcd_stage_nchw_to_f32: bad arguments");
+    const long long npix = 1LL * N * H * W;
+    stage_f32_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, C, Cp, 1LL * H * W, npix, dst, dst_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_f32_to_split(const float* src, int src_ld, void* dst_hi, void* dst_lo, int dst_ld, long long npix, int Cp,
+                     void* stream) {
+    FCD_CHECK_ARG(src && dst_hi && Cp % 8 == 0 && src_ld % 4 == 0 && dst_ld % 8 == 0, "fcd_f32_to_split: bad arguments");
+    f32_to_split_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(src, src_ld, BF(dst_hi), BF(dst_lo),
+                                                                                    dst_ld, npix, Cp);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_add_f32(float* dst, int dst_ld, const float* src, int src_ld, long long npix, int Cp, void* stream) {
+    FCD_CHECK_ARG(dst && src && Cp % 8 == 0 && dst_ld % 4 == 0 && src_ld % 4 == 0, "fcd_add_f32: bad arguments");
+    add_f32_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(dst, dst_ld, src, src_ld, npix, Cp);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_stats(const float* z, int z_ld, long long npix, int Cp, double* sum, double* sqsum, void* stream) {
+    FCD_CHECK_ARG(z && sum && sqsum, "fcd_bn_stats: null pointer");
+    const int cg = Cp / 8;
+    FCD_CHECK_ARG(Cp % 8 == 0 && cg <= NT && NT % cg == 0, "fcd_bn_stats: Cp/8 must divide 256 (Cp=%d)", Cp);
+    bn_stats_kernel<<<reduce_grid(npix, NT / cg), NT, 0, as_stream(stream)>>>(z, z_ld, npix, Cp, sum, sqsum);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int C, int Cp, float momentum, float eps, int training,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream) {
+    FCD_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && mean && invstd,
+                  "fcd_bn_finalize: null pointer");
+    FCD_CHECK_ARG(!training || (sum && sqsum && count > 0), "fcd_bn_finalize: training mode needs statistics");
+    bn_finalize_kernel<<<(Cp + 127) / 128, 128, 0, as_stream(stream)>>>(sum, sqsum, count, gamma, beta, running_mean,
+                                                                        running_var, C, Cp, momentum, eps, training,
+                                                                        scale, shift, mean, invstd);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_act_fwd(const float* z, int z_ld, const float* scale, const float* shift, int act, const float* slope_ptr,
+                   float slope_const, const void* res_hi, const void* res_lo, int res_ld, void* out_hi, void* out_lo,
+                   int out_ld, long long npix, int Cp, void* stream) {
+    FCD_CHECK_ARG(z && out_hi && Cp % 8 == 0 && z_ld % 4 == 0 && out_ld % 8 == 0, "fcd_bn_act_fwd: bad arguments");
+    FCD_CHECK_ARG((scale == nullptr) == (shift == nullptr), "fcd_bn_act_fwd: scale and shift go together");
+    bn_act_fwd_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        z, z_ld, scale, shift, act, slope_ptr, slope_const, CBF(res_hi), CBF(res_lo), res_ld, BF(out_hi), BF(out_lo),
+        out_ld, npix, Cp);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_act_bwd_reduce(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, int act, const float* slope_ptr, float slope_const,
+                          long long npix, int Cp, double* s1, double* s2, double* dslope, void* stream) {
+    FCD_CHECK_ARG(da && z && s1 && s2, "fcd_bn_act_bwd_reduce: null pointer");
+    const int cg = Cp / 8;
+    FCD_CHECK_ARG(Cp % 8 == 0 && cg <= NT && NT % cg == 0, "fcd_bn_act_bwd_reduce: Cp/8 must divide 256 (Cp=%d)", Cp);
+    bn_act_bwd_reduce_kernel<<<reduce_grid(npix, NT / cg), NT, 0, as_stream(stream)>>>(
+        da, da_ld, z, z_ld, scale, shift, mean, invstd, act, slope_ptr, slope_const, npix, Cp, s1, s2, dslope);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_bwd_finalize(const double* s1, const double* s2, double count, int training, int C, int Cp, float* c1,
+                        float* c2, float* dgamma, float* dbeta, int accumulate, const double* ds, float* dslope,
+                        void* stream) {
+    FCD_CHECK_ARG(s1 && s2 && c1 && c2 && count > 0, "fcd_bn_bwd_finalize: bad arguments");
+    bn_bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, as_stream(stream)>>>(s1, s2, count, training, C, Cp, c1, c2,
+                                                                            dgamma, dbeta, accumulate, ds, dslope);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_bn_act_bwd_apply(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* c1, const float* c2, int act,
+                         const float* slope_ptr, float slope_const, void* dz_hi, void* dz_lo, int dz_ld, long long npix,
+                         int Cp, void* stream) {
+    FCD_CHECK_ARG(da && dz_hi && Cp % 8 == 0, "fcd_bn_act_bwd_apply: bad arguments");
+    FCD_CHECK_ARG(!scale || (z && shift && mean && invstd && c1 && c2), "fcd_bn_act_bwd_apply: BN path needs all vectors");
+    FCD_CHECK_ARG(act == FCD_ACT_NONE || z, "fcd_bn_act_bwd_apply: activation backward needs z");
+    bn_act_bwd_apply_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        da, da_ld, z, z_ld, scale, shift, mean, invstd, c1, c2, act, slope_ptr, slope_const, BF(dz_hi), BF(dz_lo), dz_ld,
+        npix, Cp);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_maxpool2_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int H, int W, int Cp, void* out_hi,
+                     void* out_lo, int out_ld, void* stream) {
+    FCD_CHECK_ARG(in_hi && out_hi && H >= 2 && W >= 2 && Cp % 8 == 0, "fcd_maxpool2_fwd: bad arguments");
+    maxpool_fwd_kernel<<<blocks_for(1LL * N * (H / 2) * (W / 2) * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, BF(out_hi), BF(out_lo), out_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_maxpool2_bwd(const float* d_out, int dout_ld, const void* in_hi, const void* in_lo, int in_ld, int N, int H,
+                     int W, int Cp, float* d_in, int din_ld, int accumulate, void* stream) {
+    FCD_CHECK_ARG(d_out && in_hi && d_in && Cp % 8 == 0, "fcd_maxpool2_bwd: bad arguments");
+    maxpool_bwd_kernel<<<blocks_for(1LL * N * H * W * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        d_out, dout_ld, CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, d_in, din_ld, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_upsample2x_bilinear_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int h, int w, int Cp,
+                                void* out_hi, void* out_lo, int out_ld, int H, int W, int pad_top, int pad_left,
+                                void* stream) {
+    FCD_CHECK_ARG(in_hi && out_hi && Cp % 8 == 0 && H >= 2 * h + pad_top && W >= 2 * w + pad_left && pad_top >= 0 &&
+                      pad_left >= 0,
+                  "fcd_upsample2x_bilinear_fwd: bad arguments");
+    upsample_fwd_kernel<<<blocks_for(1LL * N * H * W * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        CBF(in_hi), CBF(in_lo), in_ld, N, h, w, Cp, BF(out_hi), BF(out_lo), out_ld, H, W, pad_top, pad_left);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_upsample2x_bilinear_bwd(const float* d_out, int dout_ld, int N, int h, int w, int Cp, int H, int W, int pad_top,
+                                int pad_left, float* d_in, int din_ld, void* stream) {
+    FCD_CHECK_ARG(d_out && d_in && Cp % 8 == 0, "fcd_upsample2x_bilinear_bwd: bad arguments");
+    upsample_bwd_kernel<<<blocks_for(1LL * N * h * w * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, d_in, din_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_convT2x2_shuffle_fwd(const float* src, long long plane_stride, int src_ld, int N, int h, int w, int Cp,
+                             void* out_hi, void* out_lo, int out_ld, int H, int W, int pad_top, int pad_left,
+                             void* stream) {
+    FCD_CHECK_ARG(src && out_hi && Cp % 8 == 0, "fcd_convT2x2_shuffle_fwd: bad arguments");
+    shuffle_up_kernel<<<blocks_for(1LL * N * H * W * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        src, plane_stride, src_ld, N, h, w, Cp, BF(out_hi), BF(out_lo), out_ld, H, W, pad_top, pad_left);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_convT2x2_shuffle_bwd(const float* d_out, int dout_ld, int N, int h, int w, int Cp, int H, int W, int pad_top,
+                             int pad_left, void* g_hi, void* g_lo, long long plane_stride, int g_ld, void* stream) {
+    FCD_CHECK_ARG(d_out && g_hi && Cp % 8 == 0, "fcd_convT2x2_shuffle_bwd: bad arguments");
+    shuffle_down_kernel<<<blocks_for(4LL * N * h * w * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, BF(g_hi), BF(g_lo), plane_stride, g_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+}  // extern "C"

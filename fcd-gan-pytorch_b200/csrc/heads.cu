@@ -1,0 +1,359 @@
+// heads.cu — the small heads and the inline masking arithmetic of the training loops:
+//   * OutConv: Conv2d 1x1 (128 -> n_out) + Sigmoid producing the change-density map   (Module.py:82-90)
+//   * Discriminator classifier: AdaptiveAvgPool2d(1) of (fx - fy), two 1x1 convs (= dense layers) with
+//     LeakyReLU(0.2) between, sigmoid                                                 (Module.py:212-223)
+//   * soft masking x*(1-cmap) and the fake-unchanged synthesis y*(1-region)+x*region
+//                                                       (Demo_RSSS.py:290-300, Demo_WSSS.py:261-279)
+// All are HBM-bound: one pass over the activations, warp-shuffle reductions, double atomics for the
+// few parameter-gradient sums.
+#include "fcd_common.cuh"
+
+namespace fcd {
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- OutConv -------------------------------------------------------------------------------------
+// one warp per pixel; lane handles channels lane*4 .. +3 (+128 per round); n_out <= 4
+__global__ void outconv_fwd_kernel(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int x_ld, int Cin,
+                                   const float* __restrict__ w, const float* __restrict__ b, int n_out, long long npix,
+                                   long long HW, float* __restrict__ out /* NCHW (N,n_out,H,W) */) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (gridDim.x * 1LL * blockDim.x) >> 5;
+    for (long long pix = warp; pix < npix; pix += nwarps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = lane * 4; c < Cin; c += 128) {
+            const size_t off = static_cast<size_t>(pix) * x_ld + c;
+            float v[4];
+            const uint2 h = *reinterpret_cast<const uint2*>(x_hi + off);
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+            float2 a = __bfloat1622float2(hp[0]), bb = __bfloat1622float2(hp[1]);
+            v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y;
+            if (x_lo) {
+                const uint2 l = *reinterpret_cast<const uint2*>(x_lo + off);
+                const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+                a = __bfloat1622float2(lp[0]); bb = __bfloat1622float2(lp[1]);
+                v[0] += a.x; v[1] += a.y; v[2] += bb.x; v[3] += bb.y;
+            }
+            for (int o = 0; o < n_out; ++o) {
+                const float4 ww = *reinterpret_cast<const float4*>(w + o * Cin + c);
+                acc[o] += v[0] * ww.x + v[1] * ww.y + v[2] * ww.z + v[3] * ww.w;
+            }
+        }
+        for (int o = 0; o < n_out; ++o) acc[o] = warp_sum(acc[o]);
+        if (lane == 0) {
+            const long long n = pix / HW, p = pix - n * HW;
+            for (int o = 0; o < n_out; ++o) out[(n * n_out + o) * HW + p] = sigmoidf_(acc[o] + b[o]);
+        }
+    }
+}
+
+// dlogit = dout * s * (1 - s);  dx[pix][c] = sum_o dlogit_o w[o][c];  dw[o][c] += sum_pix dlogit_o x[pix][c];  db[o] += sum dlogit_o
+__global__ void outconv_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const __nv_bfloat16* x_hi,
+                                   const __nv_bfloat16* x_lo, int x_ld, int Cin, const float* __restrict__ w, int n_out,
+                                   long long npix, long long HW, float* __restrict__ dx, int dx_ld, double* dw, double* db) {
+    // block: 256 threads = 8 warps; thread owns channels lane*4.. (Cin <= 128) ; accumulates dw privately over its pixels
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp = blockIdx.x * 8LL + wid, nwarps = gridDim.x * 8LL;
+    float dwacc[4][4];
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dwacc[o][j] = 0.f;
+    const int c = lane * 4;
+    float wv[4][4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[o][j] = (o < n_out && c + j < Cin) ? w[o * Cin + c + j] : 0.f;
+    for (long long pix = warp; pix < npix; pix += nwarps) {
+        const long long n = pix / HW, p = pix - n * HW;
+        float dl[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int o = 0; o < n_out; ++o) {
+            const float s = out[(n * n_out + o) * HW + p];
+            dl[o] = dout[(n * n_out + o) * HW + p] * s * (1.f - s);
+        }
+        if (c < Cin) {
+            const size_t off = static_cast<size_t>(pix) * x_ld + c;
+            float v[4];
+            const uint2 h = *reinterpret_cast<const uint2*>(x_hi + off);
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+            float2 a = __bfloat1622float2(hp[0]), bb = __bfloat1622float2(hp[1]);
+            v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y;
+            if (x_lo) {
+                const uint2 l = *reinterpret_cast<const uint2*>(x_lo + off);
+                const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+                a = __bfloat1622float2(lp[0]); bb = __bfloat1622float2(lp[1]);
+                v[0] += a.x; v[1] += a.y; v[2] += bb.x; v[3] += bb.y;
+            }
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = fmaf(dl[o], wv[o][j], g[j]);
+                    dwacc[o][j] = fmaf(dl[o], v[j], dwacc[o][j]);
+                }
+            }
+            *reinterpret_cast<float4*>(dx + static_cast<size_t>(pix) * dx_ld + c) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        if (lane == 0)
+            for (int o = 0; o < n_out; ++o) dbacc[o] += dl[o];
+    }
+    // combine the 8 warps of the block, then one double atomic per (o, c)
+    __shared__ float red[8][4][128];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[wid][o][c + j] = dwacc[o][j];
+    __shared__ float redb[8][4];
+    if (lane == 0)
+        for (int o = 0; o < 4; ++o) redb[wid][o] = dbacc[o];
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_out * Cin; t += blockDim.x) {
+        const int o = t / Cin, cc = t % Cin;
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += red[k][o][cc];
+        atomicAdd(dw + o * Cin + cc, static_cast<double>(s));
+    }
+    if (threadIdx.x < n_out) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += redb[k][threadIdx.x];
+        atomicAdd(db + threadIdx.x, static_cast<double>(s));
+    }
+}
+
+__global__ void double_to_float_kernel(const double* src, float* dst, int n, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (accumulate ? dst[i] : 0.f) + static_cast<float>(src[i]);
+}
+
+// ---- discriminator head ----------------------------------------------------------------------------
+// pooled[n][c] = mean_{h,w}(fx - fy); grid (N, C/8 groups / per-block), simple strided loop
+__global__ void gap_diff_fwd_kernel(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const __nv_bfloat16* y_hi,
+                                    const __nv_bfloat16* y_lo, int ld, int HW, int C, float* pooled) {
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int py = threadIdx.x >> 5;  // 8 pixel lanes
+    float acc = 0.f;
+    if (c < C) {
+        SplitCPtr X{x_hi, x_lo}, Y{y_hi, y_lo};
+        for (int p = py; p < HW; p += 8) {
+            const size_t off = (static_cast<size_t>(n) * HW + p) * ld + c;
+            acc += load_split(X, off) - load_split(Y, off);
+        }
+    }
+    __shared__ float red[8][32];
+    red[py][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (py == 0 && c < C) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        pooled[n * C + c] = s / HW;
+    }
+}
+
+// d_fx[n,p,c] = dpooled[n][c]/HW, d_fy = -d_fx  (fp32 NHWC)
+__global__ void gap_diff_bwd_kernel(const float* __restrict__ dpooled, int HW, int C, long long total, float* dfx,
+                                    float* dfy, int ld) {
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    const long long pix = idx / C;
+    const long long n = pix / HW;
+    const float g = dpooled[n * C + c] / HW;
+    dfx[pix * ld + c] = g;
+    dfy[pix * ld + c] = -g;
+}
+
+// dense layer: out[n][o] = act(b[o] + sum_i in[n][i] w[o][i]); one warp per (n, o).  act: 0 none, 3 leaky(0.2), 4 sigmoid
+__global__ void fc_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b, int N,
+                              int I, int O, int act, float* __restrict__ pre, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= 1LL * N * O) return;
+    const int n = static_cast<int>(warp / O), o = static_cast<int>(warp % O);
+    float acc = 0.f;
+    for (int i = lane; i < I; i += 32) acc = fmaf(in[n * I + i], w[static_cast<size_t>(o) * I + i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float u = acc + b[o];
+        if (pre) pre[n * O + o] = u;
+        out[n * O + o] = act == 3 ? (u > 0.f ? u : 0.2f * u) : act == 4 ? sigmoidf_(u) : u;
+    }
+}
+
+// du[n][o] = dout[n][o] * act'(.)   (for sigmoid uses out; for leaky uses pre)
+__global__ void fc_bwd_act_kernel(const float* dout, const float* pre, const float* out, int total, int act, float* du) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float g = dout[i];
+    if (act == 3) g *= (pre[i] > 0.f ? 1.f : 0.2f);
+    else if (act == 4) g *= out[i] * (1.f - out[i]);
+    du[i] = g;
+}
+// din[n][i] = sum_o du[n][o] w[o][i]
+__global__ void fc_bwd_input_kernel(const float* __restrict__ du, const float* __restrict__ w, int N, int I, int O,
+                                    float* __restrict__ din) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * I) return;
+    const int n = idx / I, i = idx % I;
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) acc = fmaf(du[n * O + o], w[static_cast<size_t>(o) * I + i], acc);
+    din[idx] = acc;
+}
+// dw[o][i] (+)= sum_n du[n][o] in[n][i];  db[o] (+)= sum_n du[n][o]
+__global__ void fc_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int N, int I, int O,
+                                     float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= 1LL * O * I) return;
+    const int o = static_cast<int>(idx / I), i = static_cast<int>(idx % I);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(du[n * O + o], in[n * I + i], acc);
+    dw[idx] = (accumulate ? dw[idx] : 0.f) + acc;
+    if (i == 0) {
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s += du[n * O + o];
+        db[o] = (accumulate ? db[o] : 0.f) + s;
+    }
+}
+
+// ---- masking (NCHW fp32, boundary level) -------------------------------------------------------------
+// out = (a*(1-r) + b*r) * (1 - m)     with r = region (optional, b optional), m = mask (N,1,H,W)
+__global__ void mask_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ region,
+                                const float* __restrict__ m, int C, long long HW, long long total, float* __restrict__ out) {
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long p = idx % HW;
+    const long long n = idx / (HW * C);
+    float v = a[idx];
+    if (region) {
+        const float r = region[n * HW + p];
+        v = v * (1.f - r) + b[idx] * r;
+    }
+    out[idx] = v * (1.f - m[n * HW + p]);
+}
+// dm[n,p] (+)= -sum_c dout * (a*(1-r)+b*r);   one thread per pixel
+__global__ void mask_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ region, int C, long long HW, long long npix,
+                                float* __restrict__ dm, int accumulate) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long n = pix / HW, p = pix - n * HW;
+    const float r = region ? region[pix] : 0.f;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const long long i = (n * C + c) * HW + p;
+        float v = a[i];
+        if (region) v = v * (1.f - r) + b[i] * r;
+        acc = fmaf(dout[i], v, acc);
+    }
+    dm[pix] = (accumulate ? dm[pix] : 0.f) - acc;
+}
+
+inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + NT - 1) / NT); }
+
+}  // namespace
+}  // namespace fcd
+
+using namespace fcd;
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int fcd_outconv_sigmoid_fwd(const void* x_hi, const void* x_lo, int x_ld, int Cin, const float* w, const float* b,
+                            int n_out, int N, int H, int W, float* out_nchw, void* stream) {
+    FCD_CHECK_ARG(x_hi && w && b && out_nchw, "fcd_outconv_sigmoid_fwd: null pointer");
+    FCD_CHECK_ARG(n_out >= 1 && n_out <= 4 && Cin % 4 == 0 && x_ld % 4 == 0, "fcd_outconv_sigmoid_fwd: n_out in 1..4, Cin %% 4");
+    const long long npix = 1LL * N * H * W;
+    long long blocks = (npix + 7) / 8;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    outconv_fwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, as_stream(stream)>>>(CBF(x_hi), CBF(x_lo), x_ld, Cin, w, b,
+                                                                                    n_out, npix, 1LL * H * W, out_nchw);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+// scratch: double[n_out*Cin + n_out], zeroed here.
+int fcd_outconv_sigmoid_bwd(const float* dout_nchw, const float* out_nchw, const void* x_hi, const void* x_lo, int x_ld,
+                            int Cin, const float* w, int n_out, int N, int H, int W, float* dx, int dx_ld, float* dw,
+                            float* db, int accumulate, double* scratch, void* stream) {
+    FCD_CHECK_ARG(dout_nchw && out_nchw && x_hi && w && dx && dw && db && scratch, "fcd_outconv_sigmoid_bwd: null pointer");
+    FCD_CHECK_ARG(n_out >= 1 && n_out <= 4 && Cin % 4 == 0 && Cin <= 128 && dx_ld % 4 == 0,
+                  "fcd_outconv_sigmoid_bwd: n_out in 1..4, Cin <= 128");
+    cudaStream_t s = as_stream(stream);
+    FCD_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * (n_out * Cin + n_out), s));
+    const long long npix = 1LL * N * H * W;
+    long long blocks = (npix + 63) / 64;
+    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+    outconv_bwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w,
+                                                                    n_out, npix, 1LL * H * W, dx, dx_ld, scratch,
+                                                                    scratch + n_out * Cin);
+    FCD_LAUNCH_OK();
+    double_to_float_kernel<<<(n_out * Cin + 127) / 128, 128, 0, s>>>(scratch, dw, n_out * Cin, accumulate);
+    double_to_float_kernel<<<1, 32, 0, s>>>(scratch + n_out * Cin, db, n_out, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_gap_diff_fwd(const void* x_hi, const void* x_lo, const void* y_hi, const void* y_lo, int ld, int N, int HW, int C,
+                     float* pooled, void* stream) {
+    FCD_CHECK_ARG(x_hi && y_hi && pooled, "fcd_gap_diff_fwd: null pointer");
+    gap_diff_fwd_kernel<<<dim3((C + 31) / 32, N), NT, 0, as_stream(stream)>>>(CBF(x_hi), CBF(x_lo), CBF(y_hi), CBF(y_lo), ld,
+                                                                              HW, C, pooled);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_gap_diff_bwd(const float* dpooled, int N, int HW, int C, float* dfx, float* dfy, int ld, void* stream) {
+    FCD_CHECK_ARG(dpooled && dfx && dfy, "fcd_gap_diff_bwd: null pointer");
+    const long long total = 1LL * N * HW * C;
+    gap_diff_bwd_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(dpooled, HW, C, total, dfx, dfy, ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_fc_fwd(const float* in, const float* w, const float* b, int N, int I, int O, int act, float* pre, float* out,
+               void* stream) {
+    FCD_CHECK_ARG(in && w && b && out, "fcd_fc_fwd: null pointer");
+    fc_fwd_kernel<<<blocks_for(32LL * N * O), NT, 0, as_stream(stream)>>>(in, w, b, N, I, O, act, pre, out);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+// du is caller scratch of N*O floats
+int fcd_fc_bwd(const float* dout, const float* pre, const float* out, const float* in, const float* w, int N, int I, int O,
+               int act, float* du, float* din, float* dw, float* db, int accumulate, void* stream) {
+    FCD_CHECK_ARG(dout && in && w && du && dw && db, "fcd_fc_bwd: null pointer");
+    cudaStream_t s = as_stream(stream);
+    fc_bwd_act_kernel<<<(N * O + NT - 1) / NT, NT, 0, s>>>(dout, pre, out, N * O, act, du);
+    if (din) fc_bwd_input_kernel<<<(N * I + NT - 1) / NT, NT, 0, s>>>(du, w, N, I, O, din);
+    fc_bwd_weight_kernel<<<blocks_for(1LL * O * I), NT, 0, s>>>(du, in, N, I, O, dw, db, accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_mask_fwd(const float* a, const float* b, const float* region, const float* mask, int N, int C, int H, int W,
+                 float* out, void* stream) {
+    FCD_CHECK_ARG(a && mask && out && ((region == nullptr) == (b == nullptr)), "fcd_mask_fwd: bad arguments");
+    const long long total = 1LL * N * C * H * W;
+    mask_fwd_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(a, b, region, mask, C, 1LL * H * W, total, out);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_mask_bwd(const float* dout, const float* a, const float* b, const float* region, int N, int C, int H, int W,
+                 float* dmask, int accumulate, void* stream) {
+    FCD_CHECK_ARG(dout && a && dmask, "fcd_mask_bwd: null pointer");
+    const long long npix = 1LL * N * H * W;
+    mask_bwd_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(dout, a, b, region, C, 1LL * H * W, npix, dmask,
+                                                                    accumulate);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,628 @@
+"""Internal NHWC execution engine behind the reference-named nn.Modules (modules.py).
+
+Inside a network everything is NHWC and channel padded; NCHW fp32 exists only at the module boundary
+(SURVEY.md §8(b)).  A network forward is a sequence of C-ABI kernel launches (include/fcd_b200.h) recorded
+on a `Tape`; the tape's closures, run in reverse, are the hand-written backward pass.  torch supplies
+device memory (caching allocator), the current stream and the autograd hook (`NetFunction`) only.
+
+Tensors
+  * `Act`  split activation: two bf16 NHWC planes (hi, lo), value = hi + lo (lo is None in "fast" precision).
+           Convolution operands.  May be a channel slice of a concatenation buffer (pitch `ld` > Cp).
+  * `Z`    raw convolution output, fp32 NHWC, plus the per-channel sum / sum-of-squares for BatchNorm.
+  * gradients w.r.t. an `Act` are fp32 NHWC (`Act.grad`), gradients w.r.t. a `Z` are split (`Z.dz`), because
+    they are the operands of the dgrad / wgrad convolutions.
+
+There is no CPU or torch fallback here: every arithmetic step is a libfcd_b200.so call and raises if the
+library is missing (`_lib.FcdError`).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LEAKY = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
+BN_MOMENTUM = 0.1
+
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": False}
+launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
+
+
+def set_precision(mode: str) -> None:
+    """'parity': split-bf16 operands, three tcgen05 MMAs per product (fp32-class accuracy, the mode the 1e-3
+    change-density parity bar is checked in).  'fast': single bf16 plane, one MMA (throughput mode)."""
+    if mode not in ("parity", "fast"):
+        raise ValueError("precision must be 'parity' or 'fast'")
+    _cfg["split"] = mode == "parity"
+
+
+def get_precision() -> str:
+    return "parity" if _cfg["split"] else "fast"
+
+
+def set_engine(engine: int) -> None:
+    _cfg["engine"] = engine
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    return _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+
+
+def pad_ch(c: int) -> int:
+    """Channel padding rule: multiples of 64 stay (tcgen05 path), small counts round up to 16 (SIMT path)."""
+    return (c + 63) // 64 * 64 if c >= 64 else (c + 15) // 16 * 16
+
+
+# --------------------------------------------------------------------------------------------------
+class Act:
+    """Split NHWC activation view (possibly a channel slice of a wider buffer)."""
+
+    __slots__ = ("hi", "lo", "N", "H", "W", "C", "Cp", "ld", "parent", "off", "_grad", "_ready", "name")
+
+    def __init__(self, hi, lo, N, H, W, C, Cp, ld, parent=None, off=0, name=""):
+        self.hi, self.lo = hi, lo
+        self.N, self.H, self.W, self.C, self.Cp, self.ld = N, H, W, C, Cp, ld
+        self.parent, self.off = parent, off
+        self._grad = None
+        self._ready = False
+        self.name = name
+
+    @staticmethod
+    def empty(N, H, W, C, device, Cp=None, name="") -> "Act":
+        Cp = Cp or pad_ch(C)
+        hi = torch.empty((N, H, W, Cp), dtype=torch.bfloat16, device=device)
+        lo = torch.empty_like(hi) if _cfg["split"] else None
+        return Act(hi, lo, N, H, W, C, Cp, Cp, name=name)
+
+    def slice(self, off: int, C: int) -> "Act":
+        assert off % 8 == 0 and C % 8 == 0 and off + C <= self.Cp
+        return Act(self.hi[..., off:off + C], None if self.lo is None else self.lo[..., off:off + C], self.N,
+                   self.H, self.W, C, C, self.ld, parent=self, off=off, name=f"{self.name}[{off}:{off + C}]")
+
+    @property
+    def npix(self) -> int:
+        return self.N * self.H * self.W
+
+    def p_hi(self):
+        return self.hi.data_ptr()
+
+    def p_lo(self):
+        return None if self.lo is None else self.lo.data_ptr()
+
+    # ---- gradient buffer (fp32 NHWC, same pitch as the data) ----
+    @property
+    def grad(self) -> torch.Tensor:
+        if self._grad is None:
+            if self.parent is not None:
+                self._grad = self.parent.grad[..., self.off:self.off + self.Cp]
+            else:
+                self._grad = torch.empty((self.N, self.H, self.W, self.Cp), dtype=torch.float32, device=self.hi.device)
+        return self._grad
+
+    @property
+    def ready(self) -> bool:
+        return self._ready or (self.parent is not None and self.parent.ready)
+
+    def mark_ready(self):
+        self._ready = True
+
+    def reset_grad(self):
+        self._grad = None
+        self._ready = False
+
+
+class Z:
+    """fp32 NHWC convolution output + BatchNorm statistics."""
+
+    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz")
+
+    def __init__(self, t, N, H, W, C, Cp):
+        self.t, self.N, self.H, self.W, self.C, self.Cp, self.ld = t, N, H, W, C, Cp, Cp
+        self.sum = self.sqsum = None
+        self.dz: Optional[Act] = None
+
+    @property
+    def npix(self):
+        return self.N * self.H * self.W
+
+
+# --------------------------------------------------------------------------------------------------
+_pack_cache: Dict[Tuple, Tuple] = {}
+_workspace: Dict[torch.device, torch.Tensor] = {}
+
+
+def clear_caches():
+    _pack_cache.clear()
+    _workspace.clear()
+
+
+def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
+    """Packed split-bf16 copy of an OIHW weight, cached until the parameter is modified in place
+    (optimizer step / load_state_dict bump `_version`)."""
+    key = (w.data_ptr(), tuple(w.shape), mode, _cfg["split"], Cout_p, Cin_p, tag)
+    ent = _pack_cache.get(key)
+    if ent is not None and ent[0] == w._version:
+        return ent[1], ent[2]
+    Cout, Cin, KH, KW = w.shape
+    rows, cols = (Cout_p, Cin_p) if mode == 0 else (Cin_p, Cout_p)
+    hi = torch.empty((KH * KW, rows, cols), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if _cfg["split"] else None
+    _call("fcd_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, Cout_p, Cin_p, mode, hi.data_ptr(), _lib.ptr(lo))
+    _pack_cache[key] = (w._version, hi, lo)
+    return hi, lo
+
+
+def _ws(device, nbytes: int) -> torch.Tensor:
+    cur = _workspace.get(device)
+    if cur is None or cur.numel() < nbytes:
+        cur = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[device] = cur
+    return cur
+
+
+def _padded_vec(v: torch.Tensor, n: int) -> torch.Tensor:
+    if v.numel() == n:
+        return v
+    out = torch.zeros(n, dtype=v.dtype, device=v.device)
+    out[:v.numel()] = v
+    return out
+
+
+class Tape:
+    """Records backward closures during a network forward; `run()` replays them in reverse.  The same tape can
+    be replayed several times (Demo_USSS.py:327 uses backward(retain_graph=True) followed by a second
+    backward), so closures never free or overwrite forward state."""
+
+    def __init__(self, device, record: bool):
+        self.device = device
+        self.record = record
+        self.ops: List[Callable[[], None]] = []
+        self.acts: List[Act] = []
+        self.pgrads: Dict[int, torch.Tensor] = {}   # id(param) -> grad (this replay)
+        self.params: Dict[int, torch.Tensor] = {}
+
+    def push(self, fn):
+        if self.record:
+            self.ops.append(fn)
+
+    def track(self, a: Act) -> Act:
+        if self.record:
+            self.acts.append(a)
+        return a
+
+    def new_act(self, N, H, W, C, Cp=None, name="") -> Act:
+        return self.track(Act.empty(N, H, W, C, self.device, Cp, name))
+
+    def pgrad(self, p: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        """(gradient buffer for parameter p, accumulate flag) — a parameter used by several layers / siamese
+        branches accumulates after its first use in this replay."""
+        k = id(p)
+        if k in self.pgrads:
+            return self.pgrads[k], 1
+        g = torch.empty_like(p, dtype=torch.float32)
+        self.pgrads[k] = g
+        self.params[k] = p
+        return g, 0
+
+    def run(self):
+        for a in self.acts:
+            a.reset_grad()
+        self.pgrads = {}
+        for fn in reversed(self.ops):
+            fn()
+        for a in self.acts:      # gradient buffers are per replay
+            a.reset_grad()
+        return self.pgrads
+
+
+# --------------------------------------------------------------------------------------------------
+# layer primitives (forward + recorded backward)
+# --------------------------------------------------------------------------------------------------
+def stage_input(tape: Tape, x: torch.Tensor, need_grad: bool, mask: Optional[torch.Tensor] = None) -> Act:
+    """NCHW fp32 boundary tensor -> split NHWC (K15)."""
+    N, C, H, W = x.shape
+    x = x.contiguous()
+    a = tape.new_act(N, H, W, C, name="input")
+    _call("fcd_stage_nchw_to_split", x.data_ptr(), _lib.ptr(mask), N, C, H, W, a.p_hi(), a.p_lo(), a.ld, a.Cp)
+    return a
+
+
+def stage_input_into(tape: Tape, x: torch.Tensor, dst: Act) -> None:
+    """Stage an NCHW fp32 tensor into an existing (slice of an) activation buffer."""
+    N, C, H, W = x.shape
+    assert (N, H, W) == (dst.N, dst.H, dst.W) and C <= dst.Cp
+    x = x.contiguous()
+    _call("fcd_stage_nchw_to_split", x.data_ptr(), None, N, C, H, W, dst.p_hi(), dst.p_lo(), dst.ld, dst.Cp)
+
+
+def act_to_nchw(tape: Tape, a: Act, grad_slot: dict) -> torch.Tensor:
+    """Split activation -> NCHW fp32 boundary tensor (output of a stand-alone building block)."""
+    out = torch.empty((a.N, a.C, a.H, a.W), dtype=torch.float32, device=tape.device)
+    _call("fcd_unstage_split_to_nchw", a.p_hi(), a.p_lo(), a.ld, a.N, a.C, a.H, a.W, out.data_ptr())
+
+    def backward():
+        dout = grad_slot["dout"].contiguous()
+        assert not a.ready
+        _call("fcd_stage_nchw_to_f32", dout.data_ptr(), a.N, a.C, a.H, a.W, a.grad.data_ptr(), a.ld, a.Cp)
+        a.mark_ready()
+
+    tape.push(backward)
+    return out
+
+
+def unstage_grad(a: Act) -> torch.Tensor:
+    """fp32 NHWC gradient of a staged input -> NCHW."""
+    out = torch.empty((a.N, a.C, a.H, a.W), dtype=torch.float32, device=a.hi.device)
+    _call("fcd_unstage_f32_to_nchw", a.grad.data_ptr(), a.ld, a.N, a.C, a.H, a.W, out.data_ptr(), 0)
+    return out
+
+
+def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride: int, pad: int, stats: bool,
+         x_needs_grad: bool = True, wtag: str = "") -> Z:
+    """nn.Conv2d forward (Module.py:26-216) + recorded wgrad/dgrad."""
+    Cout, Cin, KH, KW = w.shape
+    assert Cin == x.C, f"conv: weight expects {Cin} channels, activation has {x.C}"
+    Cout_p, Cin_p = pad_ch(Cout), x.Cp
+    N, H, W = x.N, x.H, x.W
+    OH = (H + 2 * pad - KH) // stride + 1
+    OW = (W + 2 * pad - KW) // stride + 1
+    w_hi, w_lo = _packed(w, Cout_p, Cin_p, 0, wtag)
+    bias = None if b is None else _padded_vec(b, Cout_p)
+    zt = torch.empty((N, OH, OW, Cout_p), dtype=torch.float32, device=tape.device)
+    z = Z(zt, N, OH, OW, Cout, Cout_p)
+    fuse = stats and _cfg["fuse_stats"]
+    if stats:
+        st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
+        z.sum, z.sqsum = st[0], st[1]
+    _call("fcd_conv2d_fwd", x.p_hi(), x.p_lo(), x.ld, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
+          zt.data_ptr(), z.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad,
+          z.sum.data_ptr() if fuse else None, z.sqsum.data_ptr() if fuse else None, _cfg["engine"])
+    if stats and not fuse:
+        _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
+
+    def backward():
+        dz = z.dz
+        assert dz is not None, "conv backward: output gradient missing"
+        gw, acc = tape.pgrad(w)
+        gb = None
+        if b is not None:
+            gb, accb = tape.pgrad(b)
+            assert accb == acc
+        nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
+        ws = _ws(tape.device, nbytes)
+        _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
+              N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"])
+        if x_needs_grad:
+            g = x.grad
+            addend = g.data_ptr() if x.ready else None
+            if stride == 1:
+                wd_hi, wd_lo = _packed(w, Cout_p, Cin_p, 1, wtag)
+                _call("fcd_conv2d_fwd", dz.p_hi(), dz.p_lo(), dz.ld, wd_hi.data_ptr(), _lib.ptr(wd_lo), None, addend,
+                      x.ld, g.data_ptr(), x.ld, N, OH, OW, Cout_p, Cin_p, KH, KW, 1, KH - 1 - pad, None, None,
+                      _cfg["engine"])
+            else:
+                _call("fcd_conv2d_dgrad_strided", dz.p_hi(), dz.p_lo(), dz.ld, w_hi.data_ptr(), _lib.ptr(w_lo), addend,
+                      x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad)
+            x.mark_ready()
+        z.dz = None
+
+    tape.push(backward)
+    return z
+
+
+class BN:
+    """Parameter / buffer bundle of one nn.BatchNorm2d."""
+
+    __slots__ = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
+
+    def __init__(self, weight, bias, running_mean, running_var, num_batches_tracked):
+        self.weight, self.bias = weight, bias
+        self.running_mean, self.running_var, self.num_batches_tracked = running_mean, running_var, num_batches_tracked
+
+
+def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: Optional[torch.Tensor] = None,
+           slope_const: float = 0.0, residual: Optional[Act] = None, out: Optional[Act] = None) -> Act:
+    """[BatchNorm2d] -> activation -> [+ residual], written as a split activation (K6/K7).
+    BatchNorm statistics are those of THIS call (per siamese branch)."""
+    C, Cp, npix = z.C, z.Cp, z.npix
+    dev = tape.device
+    if out is None:
+        out = tape.new_act(z.N, z.H, z.W, C, Cp)
+    vec = None
+    if bn is not None:
+        vec = torch.empty((6, Cp), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd, c1, c2
+        if training:
+            assert z.sum is not None
+        _call("fcd_bn_finalize", _lib.ptr(z.sum), _lib.ptr(z.sqsum), float(npix), bn.weight.data_ptr(),
+              bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), C, Cp, BN_MOMENTUM, BN_EPS,
+              1 if training else 0, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr())
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    sp = None if slope is None else slope.data_ptr()
+    _call("fcd_bn_act_fwd", z.t.data_ptr(), z.ld, None if vec is None else vec[0].data_ptr(),
+          None if vec is None else vec[1].data_ptr(), act, sp, slope_const,
+          None if residual is None else residual.p_hi(), None if residual is None else residual.p_lo(),
+          0 if residual is None else residual.ld, out.p_hi(), out.p_lo(), out.ld, npix, Cp)
+
+    def backward():
+        assert out.ready, f"bn_act backward: gradient of {out.name} missing"
+        da = out.grad
+        dz = Act.empty(z.N, z.H, z.W, C, dev, Cp)
+        need_reduce = bn is not None or act == ACT_PRELU
+        v = (lambda i: vec[i].data_ptr()) if vec is not None else (lambda i: None)
+        if need_reduce:
+            red = torch.zeros((2, Cp + 8), dtype=torch.float64, device=dev)
+            s1, s2, ds = red[0, :Cp], red[1, :Cp], red[0, Cp:]
+            _call("fcd_bn_act_bwd_reduce", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), act, sp,
+                  slope_const, npix, Cp, s1.data_ptr(), s2.data_ptr(), ds.data_ptr() if act == ACT_PRELU else None)
+            dgam = dbet = dsl = None
+            acc = 0
+            if bn is not None:
+                dgam, acc = tape.pgrad(bn.weight)
+                dbet, _ = tape.pgrad(bn.bias)
+            if act == ACT_PRELU:
+                dsl, acc_s = tape.pgrad(slope)
+                assert bn is None or acc_s == acc
+                acc = acc_s
+            c = vec if vec is not None else torch.empty((6, Cp), dtype=torch.float32, device=dev)
+            _call("fcd_bn_bwd_finalize", s1.data_ptr(), s2.data_ptr(), float(npix), 1 if (training and bn is not None) else 0,
+                  C, Cp, c[4].data_ptr(), c[5].data_ptr(), _lib.ptr(dgam), _lib.ptr(dbet), acc,
+                  ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl))
+        _call("fcd_bn_act_bwd_apply", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
+              sp, slope_const, dz.p_hi(), dz.p_lo(), dz.ld, npix, Cp)
+        z.dz = dz
+        if residual is not None:
+            if residual.ready:
+                _call("fcd_add_f32", residual.grad.data_ptr(), residual.ld, da.data_ptr(), out.ld, npix, Cp)
+            elif residual.parent is None and out.parent is None:
+                residual._grad = da          # alias: `out.grad` is dead after this closure
+                residual.mark_ready()
+            else:
+                residual.grad.copy_(da)
+                residual.mark_ready()
+        elif out.parent is None:
+            out.reset_grad()             # release the consumed gradient buffer early
+
+    tape.push(backward)
+    return out
+
+
+def maxpool2(tape: Tape, x: Act) -> Act:
+    """nn.MaxPool2d(2) (Module.py:44)."""
+    out = tape.new_act(x.N, x.H // 2, x.W // 2, x.C, x.Cp)
+    _call("fcd_maxpool2_fwd", x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp, out.p_hi(), out.p_lo(), out.ld)
+
+    def backward():
+        assert out.ready
+        g = x.grad
+        _call("fcd_maxpool2_bwd", out.grad.data_ptr(), out.ld, x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp,
+              g.data_ptr(), x.ld, 1 if x.ready else 0)
+        x.mark_ready()
+
+    tape.push(backward)
+    return out
+
+
+def upsample2x_into(tape: Tape, x: Act, dst: Act) -> None:
+    """nn.Upsample(x2, bilinear, align_corners=True) + F.pad + cat slot (Module.py:60,70-78)."""
+    dY, dX = dst.H - 2 * x.H, dst.W - 2 * x.W
+    pt, pl = dY // 2, dX // 2
+    assert dY >= 0 and dX >= 0 and dst.Cp == x.Cp
+    _call("fcd_upsample2x_bilinear_fwd", x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp, dst.p_hi(), dst.p_lo(), dst.ld,
+          dst.H, dst.W, pt, pl)
+
+    def backward():
+        assert dst.ready and not x.ready
+        _call("fcd_upsample2x_bilinear_bwd", dst.grad.data_ptr(), dst.ld, x.N, x.H, x.W, x.Cp, dst.H, dst.W, pt, pl,
+              x.grad.data_ptr(), x.ld)
+        x.mark_ready()
+
+    tape.push(backward)
+
+
+def conv_transpose2x2_into(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, dst: Act) -> None:
+    """nn.ConvTranspose2d(Cin, Cout, 2, 2) (Module.py:63) + F.pad + cat slot: four 1x1 tcgen05 convolutions
+    (one per output sub-pixel) and a pixel-shuffle store."""
+    Cin, Cout = w.shape[0], w.shape[1]
+    assert x.C == Cin and dst.Cp == pad_ch(Cout)
+    N, h, wd = x.N, x.H, x.W
+    Cout_p = dst.Cp
+    dY, dX = dst.H - 2 * h, dst.W - 2 * wd
+    pt, pl = dY // 2, dX // 2
+    planes = torch.empty((4, N, h, wd, Cout_p), dtype=torch.float32, device=tape.device)
+    # (Cin, Cout, 2, 2) -> four OIHW (Cout, Cin, 1, 1) matrices; tiny weight-side reshuffle
+    w4 = w.detach().permute(2, 3, 1, 0).reshape(4, Cout, Cin, 1, 1).contiguous()
+    bias = _padded_vec(b, Cout_p)
+    packed = []
+    for s in range(4):
+        hi = torch.empty((1, Cout_p, x.Cp), dtype=torch.bfloat16, device=tape.device)
+        lo = torch.empty_like(hi) if _cfg["split"] else None
+        _call("fcd_pack_conv_weight", w4[s].data_ptr(), Cout, Cin, 1, 1, Cout_p, x.Cp, 0, hi.data_ptr(), _lib.ptr(lo))
+        packed.append((hi, lo))
+        _call("fcd_conv2d_fwd", x.p_hi(), x.p_lo(), x.ld, hi.data_ptr(), _lib.ptr(lo), bias.data_ptr(), None, 0,
+              planes[s].data_ptr(), Cout_p, N, h, wd, x.Cp, Cout_p, 1, 1, 1, 0, None, None, _cfg["engine"])
+    _call("fcd_convT2x2_shuffle_fwd", planes.data_ptr(), planes.stride(0), Cout_p, N, h, wd, Cout_p, dst.p_hi(),
+          dst.p_lo(), dst.ld, dst.H, dst.W, pt, pl)
+    del planes
+
+    def backward():
+        assert dst.ready and not x.ready
+        dev = tape.device
+        g_hi = torch.empty((4, N, h, wd, Cout_p), dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty_like(g_hi) if _cfg["split"] else None
+        _call("fcd_convT2x2_shuffle_bwd", dst.grad.data_ptr(), dst.ld, N, h, wd, Cout_p, dst.H, dst.W, pt, pl,
+              g_hi.data_ptr(), _lib.ptr(g_lo), g_hi.stride(0), Cout_p)
+        dw4 = torch.empty((4, Cout, Cin), dtype=torch.float32, device=dev)
+        db4 = torch.empty((4, Cout), dtype=torch.float32, device=dev)
+        gx = x.grad
+        nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, h, wd, x.Cp, Cout_p, 1, 1, 1, 0, _cfg["engine"])
+        ws = _ws(dev, nbytes)
+        for s in range(4):
+            ghi = g_hi[s].data_ptr()
+            glo = None if g_lo is None else g_lo[s].data_ptr()
+            _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, ghi, glo, Cout_p, dw4[s].data_ptr(), db4[s].data_ptr(), N,
+                  h, wd, Cin, x.Cp, Cout, Cout_p, 1, 1, 1, 0, 0, ws.data_ptr(), nbytes, _cfg["engine"])
+            wd_hi = torch.empty((1, x.Cp, Cout_p), dtype=torch.bfloat16, device=dev)
+            wd_lo = torch.empty_like(wd_hi) if _cfg["split"] else None
+            _call("fcd_pack_conv_weight", w4[s].data_ptr(), Cout, Cin, 1, 1, Cout_p, x.Cp, 1, wd_hi.data_ptr(),
+                  _lib.ptr(wd_lo))
+            _call("fcd_conv2d_fwd", ghi, glo, Cout_p, wd_hi.data_ptr(), _lib.ptr(wd_lo), None,
+                  gx.data_ptr() if s > 0 else None, x.ld, gx.data_ptr(), x.ld, N, h, wd, Cout_p, x.Cp, 1, 1, 1, 0, None,
+                  None, _cfg["engine"])
+        x.mark_ready()
+        gw, acc = tape.pgrad(w)
+        gb, _ = tape.pgrad(b)
+        dw = dw4.reshape(2, 2, Cout, Cin).permute(3, 2, 0, 1)   # -> (Cin, Cout, 2, 2)
+        if acc:
+            gw.add_(dw)
+            gb.add_(db4.sum(0))
+        else:
+            gw.copy_(dw)
+            gb.copy_(db4.sum(0))
+
+    tape.push(backward)
+
+
+def outconv_sigmoid(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, grad_slot: dict) -> torch.Tensor:
+    """OutConv (Module.py:82-90): 1x1 conv + sigmoid -> NCHW fp32 density map.  `grad_slot['dout']` must hold the
+    NCHW output gradient when the tape is replayed."""
+    n_out, Cin = w.shape[0], w.shape[1]
+    assert Cin == x.C
+    out = torch.empty((x.N, n_out, x.H, x.W), dtype=torch.float32, device=tape.device)
+    w2 = w.reshape(n_out, Cin)
+    _call("fcd_outconv_sigmoid_fwd", x.p_hi(), x.p_lo(), x.ld, Cin, w2.data_ptr(), b.data_ptr(), n_out, x.N, x.H, x.W,
+          out.data_ptr())
+
+    def backward():
+        dout = grad_slot["dout"].contiguous()
+        gw, acc = tape.pgrad(w)
+        gb, _ = tape.pgrad(b)
+        scratch = torch.empty(n_out * Cin + n_out, dtype=torch.float64, device=tape.device)
+        assert not x.ready
+        _call("fcd_outconv_sigmoid_bwd", dout.data_ptr(), out.data_ptr(), x.p_hi(), x.p_lo(), x.ld, Cin, w2.data_ptr(),
+              n_out, x.N, x.H, x.W, x.grad.data_ptr(), x.ld, gw.data_ptr(), gb.data_ptr(), acc, scratch.data_ptr())
+        x.mark_ready()
+
+    tape.push(backward)
+    return out
+
+
+def disc_head(tape: Tape, fx: Act, fy: Act, w1, b1, w2, b2, grad_slot: dict) -> torch.Tensor:
+    """Discriminator classifier on (fx - fy) (Module.py:212-223): GAP -> 1x1(512->1024) -> LeakyReLU(0.2) ->
+    1x1(1024->1) -> sigmoid -> (B,)."""
+    N, HW, C = fx.N, fx.H * fx.W, fx.C
+    dev = tape.device
+    O1 = w1.shape[0]
+    pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+    _call("fcd_gap_diff_fwd", fx.p_hi(), fx.p_lo(), fy.p_hi(), fy.p_lo(), fx.ld, N, HW, C, pooled.data_ptr())
+    pre1 = torch.empty((N, O1), dtype=torch.float32, device=dev)
+    h1 = torch.empty_like(pre1)
+    _call("fcd_fc_fwd", pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), N, C, O1, 3, pre1.data_ptr(), h1.data_ptr())
+    out = torch.empty((N,), dtype=torch.float32, device=dev)
+    _call("fcd_fc_fwd", h1.data_ptr(), w2.data_ptr(), b2.data_ptr(), N, O1, 1, 4, None, out.data_ptr())
+
+    def backward():
+        dout = grad_slot["dout"].contiguous()
+        gw2, a2 = tape.pgrad(w2)
+        gb2, _ = tape.pgrad(b2)
+        gw1, a1 = tape.pgrad(w1)
+        gb1, _ = tape.pgrad(b1)
+        du2 = torch.empty((N,), dtype=torch.float32, device=dev)
+        dh1 = torch.empty((N, O1), dtype=torch.float32, device=dev)
+        _call("fcd_fc_bwd", dout.data_ptr(), None, out.data_ptr(), h1.data_ptr(), w2.data_ptr(), N, O1, 1, 4,
+              du2.data_ptr(), dh1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), a2)
+        du1 = torch.empty((N, O1), dtype=torch.float32, device=dev)
+        dpooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+        _call("fcd_fc_bwd", dh1.data_ptr(), pre1.data_ptr(), h1.data_ptr(), pooled.data_ptr(), w1.data_ptr(), N, C, O1, 3,
+              du1.data_ptr(), dpooled.data_ptr(), gw1.data_ptr(), gb1.data_ptr(), a1)
+        assert not fx.ready and not fy.ready and fx.ld == fy.ld
+        _call("fcd_gap_diff_bwd", dpooled.data_ptr(), N, HW, C, fx.grad.data_ptr(), fy.grad.data_ptr(), fx.ld)
+        fx.mark_ready()
+        fy.mark_ready()
+
+    tape.push(backward)
+    return out
+
+
+def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:
+    """Final convolution output (no BN / activation) -> NCHW fp32 boundary tensor (Generator block8, Module.py:168)."""
+    out = torch.empty((z.N, z.C, z.H, z.W), dtype=torch.float32, device=tape.device)
+    _call("fcd_unstage_f32_to_nchw", z.t.data_ptr(), z.ld, z.N, z.C, z.H, z.W, out.data_ptr(), 0)
+
+    def backward():
+        dout = grad_slot["dout"].contiguous()
+        dz = Act.empty(z.N, z.H, z.W, z.C, tape.device, z.Cp)
+        _call("fcd_stage_nchw_to_split", dout.data_ptr(), None, z.N, z.C, z.H, z.W, dz.p_hi(), dz.p_lo(), dz.ld, dz.Cp)
+        z.dz = dz
+
+    tape.push(backward)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd bridge
+# --------------------------------------------------------------------------------------------------
+class Runner:
+    """(forward recorder, the nn.Parameters it uses) — parameter gradients are matched by object identity."""
+
+    def __init__(self, fn, params):
+        self.fn, self.params = fn, list(params)
+
+
+def run_net(module: torch.nn.Module, fn, *inputs) -> torch.Tensor:
+    params = [p for p in module.parameters()]
+    return NetFunction.apply(Runner(fn, params), len(inputs), *inputs, *params)
+
+
+class NetFunction(torch.autograd.Function):
+    """One network forward = one autograd node.  `runner(tape, inputs, needs_input_grad) -> (outputs, finish)`
+    launches the forward kernels and records the backward closures; `finish(grad_outputs) -> input grads`
+    is called after the tape has been replayed."""
+
+    @staticmethod
+    def forward(ctx, runner, n_inputs: int, *tensors):
+        inputs = tensors[:n_inputs]
+        params = tensors[n_inputs:]
+        for t in inputs:
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise _lib.FcdError("fcdgan_b200 networks take fp32 CUDA tensors (there is no CPU path)")
+        record = any(ctx.needs_input_grad[2:])
+        tape = Tape(inputs[0].device, record)
+        outs, slot, input_acts = runner.fn(tape, inputs, ctx.needs_input_grad[2:2 + n_inputs])
+        ctx.tape, ctx.slot, ctx.input_acts = tape, slot, input_acts
+        ctx.n_inputs = n_inputs
+        ctx.param_ids = [id(p) for p in runner.params]
+        assert len(runner.params) == len(params)
+        return outs
+
+    @staticmethod
+    def backward(ctx, gout):
+        tape = ctx.tape
+        ctx.slot["dout"] = gout
+        need_in = ctx.needs_input_grad[2:2 + ctx.n_inputs]
+        # input gradients must be extracted before Tape.run() resets the gradient buffers -> do it as a final op
+        results = {}
+
+        def grab():
+            for i, a in enumerate(ctx.input_acts):
+                if need_in[i]:
+                    results[i] = unstage_grad(a)
+
+        tape.ops.insert(0, grab)
+        try:
+            pg = tape.run()
+        finally:
+            tape.ops.pop(0)
+            ctx.slot["dout"] = None
+        gin = [results.get(i) for i in range(ctx.n_inputs)]
+        gp = []
+        for k, pid in enumerate(ctx.param_ids):
+            g = pg.get(pid)
+            gp.append(g if (g is not None and ctx.needs_input_grad[2 + ctx.n_inputs + k]) else None)
+        return (None, None, *gin, *gp)

@@ -1,0 +1,343 @@
+"""Drop-in replacements for the networks of the reference's Module.py (same class names, constructor
+arguments, call signatures and state_dict keys — SURVEY.md §8(b)), executed by hand-written sm_100a kernels.
+
+The torch.nn layers created here (nn.Conv2d, nn.BatchNorm2d, nn.PReLU ...) are PARAMETER HOLDERS ONLY: they
+give the modules the reference's parameter names / shapes / default initialisation, `.to()`, `.train()`,
+`.state_dict()` and optimizer plumbing.  Their forward methods are never called; all arithmetic goes through
+`engine` (libfcd_b200.so).  A reference `.pkl` state_dict loads unchanged and vice versa.
+
+Reference: Module.py:18-223.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+
+def _bn(m: nn.BatchNorm2d) -> E.BN:
+    return E.BN(m.weight, m.bias, m.running_mean, m.running_var, m.num_batches_tracked)
+
+
+def _check_input(x: torch.Tensor, channels: int, what: str):
+    if x.dim() != 4 or x.shape[1] != channels:
+        raise ValueError(f"{what}: expected (B, {channels}, H, W), got {tuple(x.shape)}")
+
+
+# ------------------------------------------------------------------------------------------------
+# engine-level building blocks (operate on internal NHWC activations)
+# ------------------------------------------------------------------------------------------------
+def _double_conv(tape, dc: "DoubleConv", x: E.Act, training: bool, out=None, x_needs_grad=True) -> E.Act:
+    """(conv3x3 p1 -> BN -> ReLU) x 2, Module.py:18-35."""
+    seq = dc.double_conv
+    z = E.conv(tape, x, seq[0].weight, seq[0].bias, 1, 1, stats=training, x_needs_grad=x_needs_grad)
+    m = E.bn_act(tape, z, _bn(seq[1]), training, E.ACT_RELU)
+    z = E.conv(tape, m, seq[3].weight, seq[3].bias, 1, 1, stats=training)
+    return E.bn_act(tape, z, _bn(seq[4]), training, E.ACT_RELU, out=out)
+
+
+def _residual_block(tape, rb: "ResidualBlock", x: E.Act, training: bool) -> E.Act:
+    """conv-BN-PReLU-conv-BN + identity, Module.py:183-190."""
+    z = E.conv(tape, x, rb.conv1.weight, rb.conv1.bias, 1, 1, stats=training)
+    a = E.bn_act(tape, z, _bn(rb.bn1), training, E.ACT_PRELU, slope=rb.prelu.weight)
+    z = E.conv(tape, a, rb.conv2.weight, rb.conv2.bias, 1, 1, stats=training)
+    return E.bn_act(tape, z, _bn(rb.bn2), training, E.ACT_NONE, residual=x)
+
+
+# ------------------------------------------------------------------------------------------------
+class DoubleConv(nn.Module):
+    """(convolution => [BN] => ReLU) * 2 — Module.py:18-35."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        if not mid_channels:
+            mid_channels = out_channels
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(mid_channels, out_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        )
+
+    def forward(self, x):
+        _check_input(x, self.double_conv[0].in_channels, "DoubleConv")
+
+        def fn(tape, inputs, need):
+            a = E.stage_input(tape, inputs[0], need[0])
+            o = _double_conv(tape, self, a, self.training, x_needs_grad=need[0])
+            slot = {}
+            return E.act_to_nchw(tape, o, slot), slot, [a]
+
+        return E.run_net(self, fn, x)
+
+
+class Down(nn.Module):
+    """Downscaling with maxpool then double conv — Module.py:38-49."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
+
+    def forward(self, x):
+        _check_input(x, self.maxpool_conv[1].double_conv[0].in_channels, "Down")
+
+        def fn(tape, inputs, need):
+            a = E.stage_input(tape, inputs[0], need[0])
+            o = _double_conv(tape, self.maxpool_conv[1], E.maxpool2(tape, a), self.training)
+            slot = {}
+            return E.act_to_nchw(tape, o, slot), slot, [a]
+
+        return E.run_net(self, fn, x)
+
+
+class Up(nn.Module):
+    """Upscaling then double conv — Module.py:52-79.  forward(x1, x2): x1 is upsampled, zero padded to x2's
+    size and concatenated AFTER x2."""
+
+    def __init__(self, in_channels, out_channels, bilinear=False):
+        super().__init__()
+        self.bilinear = bool(bilinear)
+        if bilinear:
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+        else:
+            self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConv(in_channels, out_channels)
+
+    def _run(self, tape, x1: E.Act, cat: E.Act, up_slot: E.Act, training: bool) -> E.Act:
+        if self.bilinear:
+            E.upsample2x_into(tape, x1, up_slot)
+        else:
+            E.conv_transpose2x2_into(tape, x1, self.up.weight, self.up.bias, up_slot)
+        return _double_conv(tape, self.conv, cat, training)
+
+    def forward(self, x1, x2):
+        c1 = x1.shape[1] if self.bilinear else x1.shape[1] // 2
+        cin = self.conv.double_conv[0].in_channels
+        if x2.shape[1] + c1 != cin:
+            raise ValueError(f"Up: channels {x2.shape[1]} + {c1} do not match DoubleConv input {cin}")
+
+        def fn(tape, inputs, need):
+            a1 = E.stage_input(tape, inputs[0], need[0])
+            N, C2, H, W = inputs[1].shape
+            assert C2 % 8 == 0 and c1 % 8 == 0, "Up: channel counts must be multiples of 8"
+            cat = tape.new_act(N, H, W, C2 + c1, C2 + c1)
+            skip = tape.track(cat.slice(0, C2))
+            E.stage_input_into(tape, inputs[1], skip)
+            up_slot = tape.track(cat.slice(C2, c1))
+            o = self._run(tape, a1, cat, up_slot, self.training)
+            slot = {}
+            return E.act_to_nchw(tape, o, slot), slot, [a1, skip]
+
+        return E.run_net(self, fn, x1, x2)
+
+
+class OutConv(nn.Module):
+    """1x1 convolution + sigmoid — Module.py:82-90."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x):
+        _check_input(x, self.conv.in_channels, "OutConv")
+
+        def fn(tape, inputs, need):
+            a = E.stage_input(tape, inputs[0], need[0])
+            slot = {}
+            return E.outconv_sigmoid(tape, a, self.conv.weight, self.conv.bias, slot), slot, [a]
+
+        return E.run_net(self, fn, x)
+
+
+class Segmentor(nn.Module):
+    """Siamese U-Net producing the change-density map — Module.py:93-140.
+
+    forward(x1, x2) -> (B, n_outchannels, H, W) in [0, 1].  The shared-weight encoder is run once per temporal
+    image (BatchNorm statistics and running-stat updates are per call); each level's two
+    branch outputs and the decoder's upsampled tensor are written straight into one NHWC concatenation buffer,
+    so torch.cat (Module.py:116-132, 78) costs no copy."""
+
+    def __init__(self, n_channels, n_outchannels=1, bilinear=False):
+        super().__init__()
+        self.n_channels = n_channels
+        self.n_outchannels = n_outchannels
+        self.bilinear = bilinear
+        self.inc = DoubleConv(n_channels, 64)
+        self.down1 = Down(64, 128)
+        self.down2 = Down(128, 256)
+        self.down3 = Down(256, 512)
+        factor = 2 if bilinear else 1
+        self.down4 = Down(512, 1024 // factor)
+        self.up1 = Up(2048, 1024 // factor, bilinear)
+        self.up2 = Up(1024, 512 // factor, bilinear)
+        self.up3 = Up(512, 256 // factor, bilinear)
+        self.up4 = Up(256, 128, bilinear)
+        self.outc = OutConv(128, n_outchannels)
+
+    def forward(self, x1, x2):
+        _check_input(x1, self.n_channels, "Segmentor")
+        _check_input(x2, self.n_channels, "Segmentor")
+        if x1.shape != x2.shape:
+            raise ValueError("Segmentor: x1 and x2 must have the same shape")
+        if min(x1.shape[2], x1.shape[3]) < 16:
+            raise ValueError("Segmentor: tiles must be at least 16x16 (four 2x2 poolings)")
+
+        def fn(tape, inputs, need):
+            training = self.training
+            N, _, H, W = inputs[0].shape
+            a = E.stage_input(tape, inputs[0], need[0])
+            b = E.stage_input(tape, inputs[1], need[1])
+            enc = [self.inc, self.down1.maxpool_conv[1], self.down2.maxpool_conv[1], self.down3.maxpool_conv[1],
+                   self.down4.maxpool_conv[1]]
+            ups = [self.up4, self.up3, self.up2, self.up1]       # ups[l] consumes the level-l skip
+            ch = [m.double_conv[3].out_channels for m in enc]
+            # channels arriving from below at level l (after bilinear upsampling or the transposed conv)
+            below = [None] * 4
+            for l in range(4):
+                src = 2 * ch[4] if l == 3 else ups[l + 1].conv.double_conv[3].out_channels
+                below[l] = src if self.bilinear else src // 2
+            cats, A, B = [], [], []
+            h, w = H, W
+            for l in range(5):
+                if l > 0:
+                    h, w = h // 2, w // 2
+                tot = 2 * ch[l] + (below[l] if l < 4 else 0)
+                cat = tape.new_act(N, h, w, tot, tot, name=f"cat{l}")
+                cats.append(cat)
+                A.append(tape.track(cat.slice(0, ch[l])))
+                B.append(tape.track(cat.slice(ch[l], ch[l])))
+            for l in range(5):
+                if l == 0:
+                    _double_conv(tape, enc[0], a, training, out=A[0], x_needs_grad=need[0])
+                    _double_conv(tape, enc[0], b, training, out=B[0], x_needs_grad=need[1])
+                else:
+                    _double_conv(tape, enc[l], E.maxpool2(tape, A[l - 1]), training, out=A[l])
+                    _double_conv(tape, enc[l], E.maxpool2(tape, B[l - 1]), training, out=B[l])
+            x = cats[4]
+            for l in (3, 2, 1, 0):
+                up_slot = tape.track(cats[l].slice(2 * ch[l], below[l]))
+                x = ups[l]._run(tape, x, cats[l], up_slot, training)
+            slot = {}
+            out = E.outconv_sigmoid(tape, x, self.outc.conv.weight, self.outc.conv.bias, slot)
+            return out, slot, [a, b]
+
+        return E.run_net(self, fn, x1, x2)
+
+
+class ResidualBlock(nn.Module):
+    """Module.py:174-190."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.prelu = nn.PReLU()
+        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn2 = nn.BatchNorm2d(channels)
+
+    def forward(self, x):
+        _check_input(x, self.conv1.in_channels, "ResidualBlock")
+
+        def fn(tape, inputs, need):
+            a = E.stage_input(tape, inputs[0], need[0])
+            o = _residual_block(tape, self, a, self.training)
+            slot = {}
+            return E.act_to_nchw(tape, o, slot), slot, [a]
+
+        return E.run_net(self, fn, x)
+
+
+class Generator(nn.Module):
+    """SRGAN-style ResNet generator (no resampling, linear output) — Module.py:142-172."""
+
+    def __init__(self, n_channels):
+        super().__init__()
+        self.n_channels = n_channels
+        self.block1 = nn.Sequential(nn.Conv2d(n_channels, 64, kernel_size=9, padding=4), nn.PReLU())
+        self.block2 = ResidualBlock(64)
+        self.block3 = ResidualBlock(64)
+        self.block4 = ResidualBlock(64)
+        self.block5 = ResidualBlock(64)
+        self.block6 = ResidualBlock(64)
+        self.block7 = nn.Sequential(nn.Conv2d(64, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64))
+        self.block8 = nn.Conv2d(64, n_channels, kernel_size=9, padding=4)
+
+    def forward(self, x):
+        _check_input(x, self.n_channels, "Generator")
+
+        def fn(tape, inputs, need):
+            training = self.training
+            a = E.stage_input(tape, inputs[0], need[0])
+            z = E.conv(tape, a, self.block1[0].weight, self.block1[0].bias, 1, 4, stats=False, x_needs_grad=need[0])
+            b1 = E.bn_act(tape, z, None, training, E.ACT_PRELU, slope=self.block1[1].weight)
+            h = b1
+            for blk in (self.block2, self.block3, self.block4, self.block5, self.block6):
+                h = _residual_block(tape, blk, h, training)
+            z = E.conv(tape, h, self.block7[0].weight, self.block7[0].bias, 1, 1, stats=training)
+            s = E.bn_act(tape, z, _bn(self.block7[1]), training, E.ACT_NONE, residual=b1)   # block1 + block7
+            z = E.conv(tape, s, self.block8.weight, self.block8.bias, 1, 4, stats=False)
+            slot = {}
+            return E.z_to_nchw(tape, z, slot), slot, [a]
+
+        return E.run_net(self, fn, x)
+
+
+class Discriminator_SRGAN_simple(nn.Module):
+    """Siamese global discriminator — Module.py:192-223.  forward(x, y) -> (B,) sigmoid scores."""
+
+    def __init__(self, n_channels=3):
+        super().__init__()
+        self.n_channels = n_channels
+        self.net = nn.Sequential(
+            nn.Conv2d(n_channels, 64, kernel_size=3, stride=2, padding=1),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(64, 128, kernel_size=3, stride=2, padding=1),
+            nn.BatchNorm2d(128),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(128, 256, kernel_size=3, stride=2, padding=1),
+            nn.BatchNorm2d(256),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(256, 512, kernel_size=3, stride=2, padding=1),
+            nn.BatchNorm2d(512),
+            nn.LeakyReLU(0.2, inplace=True),
+        )
+        self.classifier = nn.Sequential(
+            nn.AdaptiveAvgPool2d(1),
+            nn.Conv2d(512, 1024, kernel_size=1),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(1024, 1, kernel_size=1),
+        )
+        self.sigmoid = nn.Sigmoid()
+
+    def _features(self, tape, a: E.Act, training: bool, need_in: bool) -> E.Act:
+        net = self.net
+        z = E.conv(tape, a, net[0].weight, net[0].bias, 2, 1, stats=False, x_needs_grad=need_in)
+        h = E.bn_act(tape, z, None, training, E.ACT_LEAKY, slope_const=0.2)
+        for ci, bi in ((2, 3), (5, 6), (8, 9)):
+            z = E.conv(tape, h, net[ci].weight, net[ci].bias, 2, 1, stats=training)
+            h = E.bn_act(tape, z, _bn(net[bi]), training, E.ACT_LEAKY, slope_const=0.2)
+        return h
+
+    def forward(self, x, y):
+        _check_input(x, self.n_channels, "Discriminator_SRGAN_simple")
+        _check_input(y, self.n_channels, "Discriminator_SRGAN_simple")
+        if x.shape != y.shape:
+            raise ValueError("Discriminator_SRGAN_simple: x and y must have the same shape")
+
+        def fn(tape, inputs, need):
+            training = self.training
+            a = E.stage_input(tape, inputs[0], need[0])
+            b = E.stage_input(tape, inputs[1], need[1])
+            fx = self._features(tape, a, training, need[0])
+            fy = self._features(tape, b, training, need[1])
+            c1, c3 = self.classifier[1], self.classifier[3]
+            slot = {}
+            out = E.disc_head(tape, fx, fy, c1.weight, c1.bias, c3.weight, c3.bias, slot)
+            return out, slot, [a, b]
+
+        return E.run_net(self, fn, x, y)

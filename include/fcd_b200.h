@@ -64,17 +64,19 @@ int fcd_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW,
  * With stride 1, dgrad of a convolution is this same call on dz with the mode-1 weights and
  * pad' = K-1-pad.  If stat_sum/stat_sqsum are non-NULL the per-channel sum and sum of squares of z
  * (double[Cout_p], the BatchNorm2d batch statistics of Module.py:27,30,156,178,181,200,204,208) are
- * ACCUMULATED into them.
+ * ACCUMULATED into them.  `addend` (optional, fp32 NHWC, pitch addend_ld) is added to z in the epilogue:
+ * it carries the identity branch of a residual block (Module.py:190) through dgrad and sums the
+ * gradients of an activation that has two consumers.
  */
 int fcd_conv2d_fwd(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
-                   const float* bias, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH,
+                   const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH,
                    int KW, int stride, int pad, double* stat_sum, double* stat_sqsum, int engine, void* stream);
 
 /* dgrad for stride-2 convolutions (Module.py:196-207 backward w.r.t. the input):
  * dx[n,h,w,ci] = sum_{r,s,co : (h+pad-r)%2==0,...} dz[n,(h+pad-r)/2,(w+pad-s)/2,co] * w[r*KW+s][co][ci]
  * w are the FORWARD (mode 0) packed weights. */
 int fcd_conv2d_dgrad_strided(const void* dz_hi, const void* dz_lo, int dz_ld, const void* w_hi, const void* w_lo,
-                             float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
+                             const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
                              int stride, int pad, void* stream);
 
 /* wgrad (nn.Conv2d backward w.r.t. weight and bias):
@@ -87,6 +89,100 @@ int fcd_conv2d_wgrad(const void* x_hi, const void* x_lo, int x_ld, const void* d
                      int dz_ld, float* dw_oihw, float* db, int N, int H, int W, int Cin, int Cin_p, int Cout,
                      int Cout_p, int KH, int KW, int stride, int pad, int accumulate, void* workspace,
                      size_t workspace_bytes, int engine, void* stream);
+
+
+/* ==== HBM-bound glue between the convolutions (elementwise.cu) =====================================
+ * "split" outputs are conv operands (bf16 hi/lo planes); fp32 NHWC tensors are conv results / gradients. */
+
+/* `.to(device)` boundary (Demo_USSS.py:147-148): NCHW fp32 (N,C,H,W) -> split NHWC with Cp >= C zero-padded
+ * channels.  `mask` (optional, (N,1,H,W)) applies x*(1-mask): the soft masking of Demo_RSSS.py:290-291. */
+int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, int H, int W, void* dst_hi, void* dst_lo,
+                            int dst_ld, int Cp, void* stream);
+/* fp32 NHWC (pitch src_ld) -> NCHW fp32; accumulate != 0 adds into dst. */
+int fcd_unstage_f32_to_nchw(const float* src, int src_ld, int N, int C, int H, int W, float* dst, int accumulate,
+                            void* stream);
+/* split NHWC -> NCHW fp32 and NCHW fp32 -> fp32 NHWC (zero padded to Cp): the boundaries of the stand-alone
+ * building blocks DoubleConv / Down / Up / ResidualBlock (Module.py:18-79,174-190). */
+int fcd_unstage_split_to_nchw(const void* src_hi, const void* src_lo, int src_ld, int N, int C, int H, int W, float* dst,
+                               void* stream);
+int fcd_stage_nchw_to_f32(const float* src, int N, int C, int H, int W, float* dst, int dst_ld, int Cp, void* stream);
+int fcd_f32_to_split(const float* src, int src_ld, void* dst_hi, void* dst_lo, int dst_ld, long long npix, int Cp,
+                     void* stream);
+/* dst[pix][c] += src[pix][c] on fp32 NHWC tensors (gradient of a tensor with two consumers, Module.py:168,190). */
+int fcd_add_f32(float* dst, int dst_ld, const float* src, int src_ld, long long npix, int Cp, void* stream);
+
+/* nn.BatchNorm2d (Module.py:27,30,156,178,181,200,204,208).  fcd_bn_stats ACCUMULATES per-channel sum / sum of
+ * squares of z into double[Cp] buffers (the tcgen05 conv epilogue can produce the same numbers);
+ * fcd_bn_finalize turns them (training != 0: batch statistics, biased variance, running stats updated with
+ * the unbiased one and `momentum`) or the running statistics (training == 0) into y = z*scale + shift. */
+int fcd_bn_stats(const float* z, int z_ld, long long npix, int Cp, double* sum, double* sqsum, void* stream);
+int fcd_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int C, int Cp, float momentum, float eps, int training,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* out = act(z*scale + shift) [+ residual]  (scale == NULL: no BN).  ReLU Module.py:28,31; PReLU 147,179
+ * (slope_ptr -> the learnable slope); LeakyReLU(0.2) 197-215 (slope_const); residual add 168,190. */
+int fcd_bn_act_fwd(const float* z, int z_ld, const float* scale, const float* shift, int act, const float* slope_ptr,
+                   float slope_const, const void* res_hi, const void* res_lo, int res_ld, void* out_hi, void* out_lo,
+                   int out_ld, long long npix, int Cp, void* stream);
+/* backward of the above in three steps: per-channel reductions (s1 = sum dy, s2 = sum dy*xhat, dslope),
+ * finalize (c1, c2, dgamma, dbeta, dslope), apply (dz written split = operand of dgrad / wgrad). */
+int fcd_bn_act_bwd_reduce(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, int act, const float* slope_ptr, float slope_const,
+                          long long npix, int Cp, double* s1, double* s2, double* dslope, void* stream);
+int fcd_bn_bwd_finalize(const double* s1, const double* s2, double count, int training, int C, int Cp, float* c1,
+                        float* c2, float* dgamma, float* dbeta, int accumulate, const double* ds, float* dslope,
+                        void* stream);
+int fcd_bn_act_bwd_apply(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* c1, const float* c2, int act,
+                         const float* slope_ptr, float slope_const, void* dz_hi, void* dz_lo, int dz_ld, long long npix,
+                         int Cp, void* stream);
+
+/* nn.MaxPool2d(2) (Module.py:44), floor semantics; backward routes to the first maximum like torch. */
+int fcd_maxpool2_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int H, int W, int Cp, void* out_hi,
+                     void* out_lo, int out_ld, void* stream);
+int fcd_maxpool2_bwd(const float* d_out, int dout_ld, const void* in_hi, const void* in_lo, int in_ld, int N, int H,
+                     int W, int Cp, float* d_in, int din_ld, int accumulate, void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip size + torch.cat (Module.py:60,70-78):
+ * writes the (N,H,W) channel slice of the concat buffer, zero outside [pad_top, pad_top+2h) x [pad_left, ..). */
+int fcd_upsample2x_bilinear_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int h, int w, int Cp,
+                                void* out_hi, void* out_lo, int out_ld, int H, int W, int pad_top, int pad_left,
+                                void* stream);
+int fcd_upsample2x_bilinear_bwd(const float* d_out, int dout_ld, int N, int h, int w, int Cp, int H, int W, int pad_top,
+                                int pad_left, float* d_in, int din_ld, void* stream);
+/* nn.ConvTranspose2d(k=2, s=2) (Module.py:63) = four 1x1 convolutions (fcd_conv2d_fwd) + these pixel shuffles. */
+int fcd_convT2x2_shuffle_fwd(const float* src, long long plane_stride, int src_ld, int N, int h, int w, int Cp,
+                             void* out_hi, void* out_lo, int out_ld, int H, int W, int pad_top, int pad_left,
+                             void* stream);
+int fcd_convT2x2_shuffle_bwd(const float* d_out, int dout_ld, int N, int h, int w, int Cp, int H, int W, int pad_top,
+                             int pad_left, void* g_hi, void* g_lo, long long plane_stride, int g_ld, void* stream);
+
+/* ==== heads and inline masking arithmetic (heads.cu) ================================================ */
+/* OutConv: Conv2d 1x1 (Cin -> n_out <= 4) + Sigmoid -> NCHW fp32 change-density map (Module.py:82-90). */
+int fcd_outconv_sigmoid_fwd(const void* x_hi, const void* x_lo, int x_ld, int Cin, const float* w, const float* b,
+                            int n_out, int N, int H, int W, float* out_nchw, void* stream);
+int fcd_outconv_sigmoid_bwd(const float* dout_nchw, const float* out_nchw, const void* x_hi, const void* x_lo, int x_ld,
+                            int Cin, const float* w, int n_out, int N, int H, int W, float* dx, int dx_ld, float* dw,
+                            float* db, int accumulate, double* scratch, void* stream);
+/* Discriminator head (Module.py:212-223): pooled = AdaptiveAvgPool2d(1)(fx - fy); dense layers with
+ * act 0 none / 3 LeakyReLU(0.2) / 4 sigmoid. */
+int fcd_gap_diff_fwd(const void* x_hi, const void* x_lo, const void* y_hi, const void* y_lo, int ld, int N, int HW, int C,
+                     float* pooled, void* stream);
+int fcd_gap_diff_bwd(const float* dpooled, int N, int HW, int C, float* dfx, float* dfy, int ld, void* stream);
+int fcd_fc_fwd(const float* in, const float* w, const float* b, int N, int I, int O, int act, float* pre, float* out,
+               void* stream);
+int fcd_fc_bwd(const float* dout, const float* pre, const float* out, const float* in, const float* w, int N, int I, int O,
+               int act, float* du, float* din, float* dw, float* db, int accumulate, void* stream);
+/* out = (a*(1-region) + b*region) * (1 - mask)  on NCHW fp32 (Demo_RSSS.py:290-300, Demo_WSSS.py:261-279);
+ * region/b optional.  Backward w.r.t. mask only (a, b are data). */
+int fcd_mask_fwd(const float* a, const float* b, const float* region, const float* mask, int N, int C, int H, int W,
+                 float* out, void* stream);
+int fcd_mask_bwd(const float* dout, const float* a, const float* b, const float* region, int N, int C, int H, int W,
+                 float* dmask, int accumulate, void* stream);
+
+/* bring-up probe for the tcgen05 shared-memory descriptor semantics (scripts/gpu_probe.py); not on the product path */
+int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks, int b_blocks,
+                         int mn_major, int n, int ksteps, int a_shift_rows, int a_base_offset, int b_shift_rows,
+                         int b_base_offset, int a_sbo, int b_sbo, void* stream);
 
 #ifdef __cplusplus
 }
