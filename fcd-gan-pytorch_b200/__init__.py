@@ -12,3 +12,6 @@ __version__ = "0.1.0"
 from .engine import get_precision, set_precision  # noqa: F401
 from .modules import (DoubleConv, Discriminator_SRGAN_simple, Down, Generator, OutConv, ResidualBlock,  # noqa: F401
                       Segmentor, Up)
+from .losses import (CGeneratorLoss, CNetLoss, PerceptionLoss, mean, mean_abs, mean_sq, region_loss,  # noqa: F401
+                     soft_mask)
+from .ssim import MS_SSIM, SSIM, ms_ssim, ssim  # noqa: F401

@@ -29,6 +29,7 @@ BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,
 BN_MOMENTUM = 0.1
 
 _cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": False}
+DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_*.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
 
@@ -133,28 +134,35 @@ class Z:
 
 
 # --------------------------------------------------------------------------------------------------
-_pack_cache: Dict[Tuple, Tuple] = {}
 _workspace: Dict[torch.device, torch.Tensor] = {}
 
 
 def clear_caches():
-    _pack_cache.clear()
     _workspace.clear()
 
 
 def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
-    """Packed split-bf16 copy of an OIHW weight, cached until the parameter is modified in place
-    (optimizer step / load_state_dict bump `_version`)."""
-    key = (w.data_ptr(), tuple(w.shape), mode, _cfg["split"], Cout_p, Cin_p, tag)
-    ent = _pack_cache.get(key)
-    if ent is not None and ent[0] == w._version:
+    """Packed split-bf16 copy of an OIHW weight.  The cache lives ON the parameter object and is valid while
+    (storage pointer, in-place version counter) are unchanged — an optimizer step, load_state_dict or .to()
+    invalidates it."""
+    cache = getattr(w, "_fcd_pack", None)
+    if cache is None:
+        cache = {}
+        try:
+            w._fcd_pack = cache
+        except AttributeError:
+            pass
+    key = (mode, _cfg["split"], Cout_p, Cin_p, tag)
+    stamp = (w.data_ptr(), w._version)
+    ent = cache.get(key)
+    if ent is not None and ent[0] == stamp:
         return ent[1], ent[2]
     Cout, Cin, KH, KW = w.shape
     rows, cols = (Cout_p, Cin_p) if mode == 0 else (Cin_p, Cout_p)
     hi = torch.empty((KH * KW, rows, cols), dtype=torch.bfloat16, device=w.device)
     lo = torch.empty_like(hi) if _cfg["split"] else None
     _call("fcd_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, Cout_p, Cin_p, mode, hi.data_ptr(), _lib.ptr(lo))
-    _pack_cache[key] = (w._version, hi, lo)
+    cache[key] = (stamp, hi, lo)
     return hi, lo
 
 
@@ -377,6 +385,10 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
         _call("fcd_bn_act_bwd_apply", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
               sp, slope_const, dz.p_hi(), dz.p_lo(), dz.ld, npix, Cp)
         z.dz = dz
+        if DEBUG_CAPTURE is not None:
+            DEBUG_CAPTURE.append(("da", da[..., :C].permute(0, 3, 1, 2).clone()))
+            j = dz.hi.float() + (dz.lo.float() if dz.lo is not None else 0)
+            DEBUG_CAPTURE.append(("dz", j[..., :C].permute(0, 3, 1, 2).clone()))
         if residual is not None:
             if residual.ready:
                 _call("fcd_add_f32", residual.grad.data_ptr(), residual.ld, da.data_ptr(), out.ld, npix, Cp)

@@ -179,6 +179,47 @@ int fcd_mask_fwd(const float* a, const float* b, const float* region, const floa
 int fcd_mask_bwd(const float* dout, const float* a, const float* b, const float* region, int N, int C, int H, int W,
                  float* dmask, int accumulate, void* stream);
 
+/* ==== loss stack (losses.cu): NCHW fp32 boundary tensors ============================================ */
+/* Masked reconstruction loss of CNetLoss (kind FCD_LOSS_L1, Loss.py:76-87) / CGeneratorLoss (FCD_LOSS_MSE,
+ * Loss.py:109-119, samples with sum(1-cmap) == 0 skipped):  out2[0] = generator_loss, out2[1] = mean|cmap|.
+ * sums: double[3*B] scratch kept for the backward (numerator_i, sum_p (1-cmap_i), sum_p |cmap_i|).
+ * tm, gm (optional): the masked images t*(1-cmap), g*(1-cmap) consumed by MS-SSIM (Loss.py:78-79,93). */
+int fcd_masked_recon_fwd(const float* t, const float* g, const float* cmap, int B, int C, int H, int W, int kind,
+                         double* sums, float* out2, float* tm, float* gm, void* stream);
+/* g_gen / g_l1: device scalars d(total)/d(generator_loss), d(total)/d(l1_loss) (NULL = 0); dtm, dgm: optional
+ * gradients w.r.t. the masked images; dt, dg, dcmap: outputs (each optional). */
+int fcd_masked_recon_bwd(const float* t, const float* g, const float* cmap, int B, int C, int H, int W, int kind,
+                         const double* sums, const float* g_gen, const float* g_l1, const float* dtm, const float* dgm,
+                         float* dt, float* dg, float* dcmap, void* stream);
+/* region_loss (Loss.py:127-141): n = elements per sample, HW = pixels per sample; sums double[2*B]. */
+int fcd_region_loss_fwd(const float* cmap, const float* region, int B, long long n, long long HW, int kind, double* sums,
+                        float* out, void* stream);
+int fcd_region_loss_bwd(const float* cmap, const float* region, int B, long long n, long long HW, int kind,
+                        const double* sums, const float* gout, float* dcmap, void* stream);
+/* mean(x) / mean|x| / mean(x^2) (mode 0/1/2): WGAN terms Demo_RSSS.py:304,324, nc_loss Demo_WSSS.py:299, l1 315. */
+int fcd_mean_fwd(const float* x, long long n, int mode, double* acc, float* out, void* stream);
+int fcd_mean_bwd(const float* x, long long n, int mode, const float* gout, float* dx, void* stream);
+/* One SSIM level (ssim.py:55-92) on planes = B*C images of H x W: separable valid Gaussian blur (win: device
+ * float[win_size], win_size odd <= 11) of X, Y, X^2, Y^2, XY; sums double[2*planes] receives the spatial SUMS of
+ * the ssim map and the cs map; dmaps (optional) float[5*planes*OH*OW] receives d(which)/d(mu1,mu2,e11,e22,e12)
+ * (which: 0 = cs, 1 = ssim) for the backward kernel. */
+int fcd_ssim_level_fwd(const float* X, const float* Y, int planes, int H, int W, const float* win, int win_size, float C1,
+                       float C2, double* sums, float* dmaps, int which, void* stream);
+/* dX, dY (+)= coef[plane] * adjoint-blur(dmaps) chain rule (autograd of ssim.py:79-91). */
+int fcd_ssim_level_bwd(const float* dmaps, const float* X, const float* Y, int planes, int H, int W, const float* win,
+                       int win_size, const float* coef, float* dX, float* dY, int accumulate, void* stream);
+/* F.avg_pool2d(kernel_size=2, padding=size%2) between MS-SSIM levels (ssim.py:215-216). */
+int fcd_avgpool2_fwd(const float* in, int planes, int H, int W, int pad_h, int pad_w, float* out, void* stream);
+int fcd_avgpool2_bwd(const float* dout, int planes, int H, int W, int pad_h, int pad_w, float* din, int accumulate,
+                     void* stream);
+/* relu / weighted geometric mean over levels / mean (ssim.py:143-150, 218-225).  sums: double[levels][2][planes];
+ * counts: device double[levels] (blurred pixels per level); prod float[planes]; out: 1 (size_average) or B values;
+ * coef float[levels][planes] = d out / d (spatial sum of the level's map). */
+int fcd_msssim_combine_fwd(const double* sums, const double* counts, const float* weights, int levels, int planes, int C,
+                           int size_average, int use_relu, float* prod, float* out, void* stream);
+int fcd_msssim_combine_bwd(const double* sums, const double* counts, const float* weights, int levels, int planes, int C,
+                           int size_average, int use_relu, const float* prod, const float* gout, float* coef, void* stream);
+
 /* bring-up probe for the tcgen05 shared-memory descriptor semantics (scripts/gpu_probe.py); not on the product path */
 int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks, int b_blocks,
                          int mn_major, int n, int ksteps, int a_shift_rows, int a_base_offset, int b_shift_rows,

@@ -1,4 +1,3 @@
 #!/bin/bash
-# first end-to-end GPU check: parity tests + verbose failures
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+timeout -s KILL 300 python scripts/dbg_g2.py 2>&1 | tail -40 | tee gpurun_out/dbg_g2.log

@@ -39,3 +39,33 @@ def check_grad_summary(named_grads, summary, tol, atol=1e-6, what=""):
         worst = max(worst, err)
         assert err <= tol, f"{what}: grad {k} rel err {err:.3g} > {tol}"
     return worst
+
+
+def check_grad_summary_l2(named_grads, summary, tol_l2, tol_max, what=""):
+    """Kink-robust comparison for END-TO-END network gradients.
+
+    A ReLU / PReLU / LeakyReLU / max-pool element whose pre-activation lies within the forward error (~1e-5) of
+    the kink takes the other one-sided derivative than the reference does (measured: the one element of
+    86,016 with |u| = 8.9e-7 in g13_train.pt, scripts/dbg_g2.py).  One such flip changes a single gradient
+    element by O(1) and leaves everything else at ~1e-5, so whole-tensor L2 error is the meaningful metric;
+    the per-kernel backward tests (tests/test_ops_gpu.py) use tight element-wise tolerances instead.
+    Gradients that are analytically zero (conv bias in front of a train-mode BatchNorm) are only required to
+    stay tiny."""
+    worst = 0.0
+    for k, ref in summary.items():
+        assert k in named_grads and named_grads[k] is not None, f"{what}: missing grad for {k}"
+        g = named_grads[k].detach().double().cpu()
+        if "full" in ref:
+            r = ref["full"].double()
+            if r.abs().max().item() < 1e-4:
+                assert g.abs().max().item() < 2e-3, f"{what}: {k} should be ~0, max |g| = {g.abs().max().item():.3g}"
+                continue
+            l2 = ((g - r).norm() / r.norm()).item()
+            mx = ((g - r).abs().max() / r.abs().max()).item()
+        else:
+            l2 = abs(g.norm().item() - ref["norm"]) / ref["norm"]
+            mx = ((g.flatten()[:16] - ref["head"].double()).abs().max() / max(ref["head"].abs().max().item(),
+                                                                             ref["norm"] / ref["numel"] ** 0.5)).item()
+        worst = max(worst, l2)
+        assert l2 <= tol_l2 and mx <= tol_max, f"{what}: grad {k} rel-L2 {l2:.3g} (tol {tol_l2}), max {mx:.3g} (tol {tol_max})"
+    return worst
