@@ -137,3 +137,26 @@ def test_step_rsss():
     assert abs(s_loss.item() - f["s_loss"]) < 5e-5 * max(1.0, abs(f["s_loss"]))
     s_loss.backward()
     check_grad_summary(_grads(sdS), f["gradsS"], 2e-3, what="rsss S")
+
+
+def test_segmentor_gradient_conditioning():
+    """Documents why END-TO-END Segmentor gradients are compared at 5e-2 on the GPU (tests/test_networks_gpu.py):
+    in the fp64 oracle itself a 1e-5 relative input perturbation (the size of the CUDA path's forward error) moves
+    dL/dx by ~1e-2 in relative L2, while the change-density map moves by ~3e-5."""
+    from tests._util import rel_l2
+    f = load_golden("s4_bilinear_odd.pt")
+
+    def run(eps):
+        sd = O.clone_sd(O.make_state_dict(O.segmentor_spec(f["C"], 1, True), f["seed"]), dtype=torch.float64)
+        x, y = f["x"].double().clone(), f["y"].double().clone()
+        if eps:
+            x = x * (1 + eps * torch.randn(x.shape, generator=torch.Generator().manual_seed(0)).double())
+        x.requires_grad_(True)
+        c = O.segmentor(sd, x, y, bilinear=True, train=True)
+        (c * f["r"].double()).sum().backward()
+        return c.detach(), x.grad
+
+    c0, g0 = run(0.0)
+    c1, g1 = run(1e-5)
+    assert rel_err(c1, c0) < 1e-3            # the parity quantity is well conditioned
+    assert 1e-3 < rel_l2(g1, g0) < 5e-2      # its gradient is not

