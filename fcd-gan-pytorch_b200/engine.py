@@ -49,15 +49,34 @@ def set_engine(engine: int) -> None:
     _cfg["engine"] = engine
 
 
-def _call(name, *args):
+PROFILE = None       # set to a list: every C-ABI call is bracketed by CUDA events -> (name, tag, flops, bytes, e0, e1)
+
+
+def _call(name, *args, tag=None, flops=0.0, nbytes=0.0):
     global launch_count
     launch_count += 1
-    return _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+    if PROFILE is None:
+        return _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+    e1.record()
+    PROFILE.append((name, tag or name, flops, nbytes, e0, e1))
+    return rc
 
 
-def pad_ch(c: int) -> int:
-    """Channel padding rule: multiples of 64 stay (tcgen05 path), small counts round up to 16 (SIMT path)."""
-    return (c + 63) // 64 * 64 if c >= 64 else (c + 15) // 16 * 16
+def _conv_engine_name(Cin_p, Cout_p, KH, KW, stride) -> str:
+    if _cfg["engine"] == ENGINE_SIMT:
+        return "simt"
+    return "tc" if _lib.load().fcd_conv2d_tc_supported(Cin_p, Cout_p, KH, KW, stride) else "simt"
+
+
+def pad_ch(c: int, tc: bool = True) -> int:
+    """Channel padding rule.  tc=True: round up to a multiple of 64 so the tensor lands on the tcgen05 engine (the
+    13-band head / tail of the Generator and the Segmentor's first layer are zero-padded to 64 channels: the padded
+    MMA work is cheaper than leaving 9x9 convolutions on CUDA cores).  tc=False: multiples of 16 (SIMT engine —
+    the stride-2 discriminator layers)."""
+    return (c + 63) // 64 * 64 if (tc or c >= 64) else (c + 15) // 16 * 16
 
 
 # --------------------------------------------------------------------------------------------------
@@ -232,11 +251,11 @@ class Tape:
 # --------------------------------------------------------------------------------------------------
 # layer primitives (forward + recorded backward)
 # --------------------------------------------------------------------------------------------------
-def stage_input(tape: Tape, x: torch.Tensor, need_grad: bool, mask: Optional[torch.Tensor] = None) -> Act:
+def stage_input(tape: Tape, x: torch.Tensor, need_grad: bool, mask: Optional[torch.Tensor] = None, tc: bool = True) -> Act:
     """NCHW fp32 boundary tensor -> split NHWC (K15)."""
     N, C, H, W = x.shape
     x = x.contiguous()
-    a = tape.new_act(N, H, W, C, name="input")
+    a = tape.new_act(N, H, W, C, Cp=pad_ch(C, tc), name="input")
     _call("fcd_stage_nchw_to_split", x.data_ptr(), _lib.ptr(mask), N, C, H, W, a.p_hi(), a.p_lo(), a.ld, a.Cp)
     return a
 
@@ -276,7 +295,7 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     """nn.Conv2d forward (Module.py:26-216) + recorded wgrad/dgrad."""
     Cout, Cin, KH, KW = w.shape
     assert Cin == x.C, f"conv: weight expects {Cin} channels, activation has {x.C}"
-    Cout_p, Cin_p = pad_ch(Cout), x.Cp
+    Cout_p, Cin_p = pad_ch(Cout, stride == 1), x.Cp
     N, H, W = x.N, x.H, x.W
     OH = (H + 2 * pad - KH) // stride + 1
     OW = (W + 2 * pad - KW) // stride + 1
@@ -288,9 +307,13 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     if stats:
         st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
         z.sum, z.sqsum = st[0], st[1]
+    eng = _conv_engine_name(Cin_p, Cout_p, KH, KW, stride)
+    flops = 2.0 * N * OH * OW * Cout * Cin * KH * KW          # algorithmic (un-padded) multiply-adds x 2
+    shape = f"{KH}x{KW}s{stride} {Cin}->{Cout}"
     _call("fcd_conv2d_fwd", x.p_hi(), x.p_lo(), x.ld, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
           zt.data_ptr(), z.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad,
-          z.sum.data_ptr() if fuse else None, z.sqsum.data_ptr() if fuse else None, _cfg["engine"])
+          z.sum.data_ptr() if fuse else None, z.sqsum.data_ptr() if fuse else None, _cfg["engine"],
+          tag=f"conv_fwd_{eng} {shape}", flops=flops)
     if stats and not fuse:
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
 
@@ -305,7 +328,8 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
         nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
         ws = _ws(tape.device, nbytes)
         _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
-              N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"])
+              N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
+              tag=f"conv_wgrad_{eng} {shape}", flops=flops)
         if x_needs_grad:
             g = x.grad
             addend = g.data_ptr() if x.ready else None
@@ -313,10 +337,11 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
                 wd_hi, wd_lo = _packed(w, Cout_p, Cin_p, 1, wtag)
                 _call("fcd_conv2d_fwd", dz.p_hi(), dz.p_lo(), dz.ld, wd_hi.data_ptr(), _lib.ptr(wd_lo), None, addend,
                       x.ld, g.data_ptr(), x.ld, N, OH, OW, Cout_p, Cin_p, KH, KW, 1, KH - 1 - pad, None, None,
-                      _cfg["engine"])
+                      _cfg["engine"], tag=f"conv_dgrad_{_conv_engine_name(Cout_p, Cin_p, KH, KW, 1)} {shape}", flops=flops)
             else:
                 _call("fcd_conv2d_dgrad_strided", dz.p_hi(), dz.p_lo(), dz.ld, w_hi.data_ptr(), _lib.ptr(w_lo), addend,
-                      x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad)
+                      x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad,
+                      tag=f"conv_dgrad_simt {shape}", flops=flops)
             x.mark_ready()
         z.dz = None
 

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 600 python __graft_entry__.py smoke 2>&1 | grep -v Warning | tail -5 | tee gpurun_out/smoke.log
+timeout -s KILL 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_parity.err | tee gpurun_out/bench_parity.json
+timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --precision fast --no-cpu-baseline 2>gpurun_out/bench_fast.err | tee gpurun_out/bench_fast.json
+tail -5 gpurun_out/bench_parity.err gpurun_out/bench_fast.err

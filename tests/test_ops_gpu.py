@@ -75,6 +75,9 @@ CONV_CASES = [
     (8, 64, 64, 64, 64, 3, 1, 1, E.ENGINE_TC),       # several tiles per CTA
     (2, 5, 4, 64, 64, 3, 1, 1, E.ENGINE_TC),         # tensor smaller than one TMA box (U-Net bottleneck)
     (2, 2, 2, 128, 64, 3, 1, 1, E.ENGINE_TC),
+    (2, 20, 24, 13, 64, 9, 1, 4, E.ENGINE_TC),       # Generator head on the tcgen05 engine (13 bands zero-padded to 64)
+    (2, 20, 24, 64, 13, 9, 1, 4, E.ENGINE_TC),       # Generator tail
+    (2, 19, 21, 4, 64, 3, 1, 1, E.ENGINE_TC),        # Segmentor first layer, 4 bands
 ]
 
 
@@ -88,11 +91,11 @@ def test_conv_fwd_wgrad_dgrad(case, fast):
     torch.manual_seed(0)
     E.set_precision("fast" if fast else "parity")
     try:
-        Cin_p, Cout_p = E.pad_ch(Cin), E.pad_ch(Cout)
+        Cin_p, Cout_p = E.pad_ch(Cin, engine == E.ENGINE_TC), E.pad_ch(Cout, engine == E.ENGINE_TC)
         x = torch.randn(N, Cin, H, W, device=DEV)
         w = torch.randn(Cout, Cin, K, K, device=DEV) * 0.1
         b = torch.randn(Cout, device=DEV)
-        a = act_from(x)
+        a = act_from(x, Cp=Cin_p)
         wh, wl = pack(w, Cout_p, Cin_p, 0)
         OH = (H + 2 * pad - K) // stride + 1
         OW = (W + 2 * pad - K) // stride + 1
@@ -113,7 +116,7 @@ def test_conv_fwd_wgrad_dgrad(case, fast):
         assert rel(st[0, :Cout], ref.sum(dim=(0, 2, 3))) < 1e-4 and rel(st[1, :Cout], (ref * ref).sum(dim=(0, 2, 3))) < 1e-4
         # ---- backward operands
         dz = torch.randn(N, Cout, OH, OW, device=DEV)
-        g = act_from(dz)
+        g = act_from(dz, Cp=Cout_p)
         gr = act_value(g)
         gx, gw = torch.autograd.grad(ref, (xr, wr), gr)
         dw = torch.full((Cout, Cin, K, K), float("nan"), device=DEV)

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: batch sharding, parameter broadcast and the
+bucketed asynchronous gradient all-reduce.  The same code runs over NCCL on the GPU box (bench.py --gpus N)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fcdgan_b200 import parallel as P
+
+
+def test_shard_batch_covers_everything():
+    for n in (1, 7, 16, 33):
+        for world in (1, 2, 4, 8):
+            got = []
+            for r in range(world):
+                s = P.shard_batch(n, r, world)
+                got += list(range(n))[s]
+            assert got == list(range(n))
+            sizes = [len(range(n)[P.shard_batch(n, r, world)]) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)          # different initial weights per rank
+    a = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+    b = torch.nn.Linear(5, 2)
+    P.broadcast_parameters([a, b])
+    w_after_bcast = a[0].weight.detach().clone()
+    # rank-dependent gradients
+    for i, p in enumerate(list(a.parameters()) + list(b.parameters())):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    sync = P.GradSync()
+    sync.start(a)
+    sync.start(b)
+    sync.finish()
+    grads = [p.grad.clone() for p in list(a.parameters()) + list(b.parameters())]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (w_after_bcast, grads))
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_two_ranks_gloo(tmp_path):
+    world = 2
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    (w0, g0), (w1, g1) = res
+    assert torch.equal(w0, w1)                                   # broadcast made the replicas identical
+    for i, (a, b) in enumerate(zip(g0, g1)):
+        assert torch.equal(a, b)
+        assert torch.allclose(a, torch.full_like(a, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
