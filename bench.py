@@ -167,21 +167,26 @@ def run_ours(args):
 
     data = synth(B, 1234 + rank, device=dev)
     # L2 note: one step streams > 20 GB of activations through a 126 MB L2, so nothing survives between steps.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()           # started BEFORE the warm-up: nvidia-smi's start-up stalls the driver for ~0.5 s
     for _ in range(args.warmup):
         step(*data)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.rows.clear()          # keep only samples taken during the timed region
     l0 = E.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         gl, dl = step(*data)
+        marks[i + 1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = E.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
@@ -222,6 +227,13 @@ def run_ours(args):
         E.PROFILE = None
         tot = sum(v[0] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        if args.profile_out:
+            with open(args.profile_out, "w") as fh:
+                fh.write(f"# per-step CUDA-event time by C-ABI call (instrumented pass, {nprof} steps, precision {args.precision}); "
+                         f"total {tot / nprof:.3f} ms/step\n# tag | ms/step | launches/step | share | TFLOP/s (algorithmic)\n")
+                for k, v in top:
+                    tf = v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 and v[2] > 0 else 0.0
+                    fh.write(f"{k:44s} {v[0] / nprof:9.3f} {v[1] // nprof:5d} {v[0] / tot:7.3f} {tf:8.1f}\n")
         pk = peaks()
         dom_tag, (dom_ms, dom_n, dom_flops, _) = top[0]
         # all tcgen05 conv launches together (the conv stack is the tensor-bound part of the step)
@@ -238,7 +250,9 @@ def run_ours(args):
                 "top5": [{"kernel": k, "ms_per_step": round(v[0] / nprof, 3), "launches": v[1] // nprof} for k, v in top[:5]]}
         cpu = cpu_baseline(bounded=True) if world == 1 and not args.no_cpu_baseline else None
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+               "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+               "ms_per_step_min_med_max": [round(per_step[0], 3), round(per_step[len(per_step) // 2], 3), round(per_step[-1], 3)],
+               "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split (fp32-class)" if args.precision == "parity" else "bf16",
                "data": "synthetic",
                "config": {"workload": "configs[1]: Generator+Discriminator fwd/bwd (+Adam/RMSprop step), batch 16/GPU of 256x256x13 "
@@ -320,6 +334,7 @@ def main():
     ap.add_argument("--precision", choices=["parity", "fast"], default="parity")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of the instrumented pass here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = run_reference(args) if args.impl == "reference" else run_ours(args)

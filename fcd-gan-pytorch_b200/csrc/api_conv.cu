@@ -28,7 +28,9 @@ int sm_count() {
 // implemented in conv_tc.cu / conv_simt.cu / wgrad_tc.cu
 bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);
 int conv2d_fwd_tc(const void*, const void*, int, const void*, const void*, const float*, const float*, int, float*, int,
-                  int, int, int, int, int, int, int, int, double*, double*, cudaStream_t);
+                  int, int, int, int, int, int, int, int, int, double*, double*, cudaStream_t);
+int conv2d_dgrad_strided_tc(const void*, const void*, int, const void*, const void*, const float*, int, float*, int, int, int,
+                            int, int, int, int, int, int, int, cudaStream_t);
 int conv2d_fwd_simt(const void*, const void*, int, const void*, const void*, const float*, const float*, int, float*,
                     int, int, int, int, int, int, int, int, int, int, double*, double*, cudaStream_t);
 int conv2d_dgrad_strided_simt(const void*, const void*, int, const void*, const void*, const float*, int, float*, int,
@@ -39,7 +41,7 @@ int pack_conv_weight(const float*, int, int, int, int, int, int, int, void*, voi
 bool wgrad_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);
 size_t wgrad_tc_workspace(int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int pad);
 int conv2d_wgrad_tc(const void*, const void*, int, const void*, const void*, int, float*, int, int, int, int, int, int,
-                    int, int, int, int, int, void*, size_t, cudaStream_t);
+                    int, int, int, int, int, int, void*, size_t, cudaStream_t);
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream);
 
@@ -78,15 +80,25 @@ int fcd_conv2d_fwd(const void* x_hi, const void* x_lo, int x_ld, const void* w_h
     }
     if (engine == FCD_ENGINE_TC || (engine == FCD_ENGINE_AUTO && tc_ok))
         return conv2d_fwd_tc(x_hi, x_lo, x_ld, w_hi, w_lo, bias, addend, addend_ld, z, z_ld, N, H, W, Cin_p, Cout_p, KH,
-                             KW, pad, stat_sum, stat_sqsum, as_stream(stream));
+                             KW, stride, pad, stat_sum, stat_sqsum, as_stream(stream));
     return conv2d_fwd_simt(x_hi, x_lo, x_ld, w_hi, w_lo, bias, addend, addend_ld, z, z_ld, N, H, W, Cin_p, Cout_p, KH,
                            KW, stride, pad, stat_sum, stat_sqsum, as_stream(stream));
 }
 
 int fcd_conv2d_dgrad_strided(const void* dz_hi, const void* dz_lo, int dz_ld, const void* w_hi, const void* w_lo,
-                             const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
-                             int stride, int pad, void* stream) {
-    FCD_CHECK_ARG(dz_hi && w_hi && dx, "fcd_conv2d_dgrad_strided: null pointer");
+                             const void* wT_hi, const void* wT_lo, const float* addend, int addend_ld, float* dx, int dx_ld,
+                             int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int stride, int pad, int engine,
+                             void* stream) {
+    FCD_CHECK_ARG(dz_hi && dx && (w_hi || wT_hi), "fcd_conv2d_dgrad_strided: null pointer");
+    const bool tc_ok = wT_hi != nullptr && conv_tc_supported(Cout_p, Cin_p, KH, KW, stride) && stride <= KH && stride <= KW;
+    if (engine == FCD_ENGINE_TC && !tc_ok) {
+        set_error(FCD_ERR_UNSUPPORTED, "fcd_conv2d_dgrad_strided: tcgen05 engine needs mode-1 weights and 64-multiple channels");
+        return FCD_ERR_UNSUPPORTED;
+    }
+    if (engine == FCD_ENGINE_TC || (engine == FCD_ENGINE_AUTO && tc_ok))
+        return conv2d_dgrad_strided_tc(dz_hi, dz_lo, dz_ld, wT_hi, wT_lo, addend, addend_ld, dx, dx_ld, N, H, W, Cin_p, Cout_p,
+                                       KH, KW, stride, pad, as_stream(stream));
+    FCD_CHECK_ARG(w_hi, "fcd_conv2d_dgrad_strided: the SIMT engine needs the mode-0 packed weights");
     return conv2d_dgrad_strided_simt(dz_hi, dz_lo, dz_ld, w_hi, w_lo, addend, addend_ld, dx, dx_ld, N, H, W, Cin_p, Cout_p, KH, KW, stride,
                                      pad, as_stream(stream));
 }
@@ -110,10 +122,10 @@ int fcd_conv2d_wgrad(const void* x_hi, const void* x_lo, int x_ld, const void* d
     }
     if (engine == FCD_ENGINE_TC || (engine == FCD_ENGINE_AUTO && tc_ok)) {
         int rc = conv2d_wgrad_tc(x_hi, x_lo, x_ld, dz_hi, dz_lo, dz_ld, dw_oihw, N, H, W, Cin, Cin_p, Cout, Cout_p, KH,
-                                 KW, pad, accumulate, workspace, workspace_bytes, as_stream(stream));
+                                 KW, stride, pad, accumulate, workspace, workspace_bytes, as_stream(stream));
         if (rc) return rc;
         if (db) {
-            const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
+            const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
             return channel_sum_split(dz_hi, dz_lo, dz_ld, 1LL * N * OH * OW, Cout, db, accumulate, as_stream(stream));
         }
         return FCD_OK;

@@ -55,9 +55,14 @@ struct ConvTcParams {
     double* stat_sum;
     double* stat_sqsum;
     int z_ld;
-    int N, OH, OW;       // output spatial dims (== input dims for stride 1 "same")
+    int N, OH, OW;       // dims of the OUTPUT tensor (addressing)
+    int TOH, TOW;        // extent of the output-pixel grid this launch covers (== OH, OW except for strided-dgrad classes)
+    int out_sh, out_oh, out_sw, out_ow;   // output pixel = (oh * out_sh + out_oh, ow * out_sw + out_ow)
     int Cin_p, Cout_p;
-    int KH, KW, pad;
+    int n_r, n_s;        // taps iterated in this launch: i in [0, n_r), j in [0, n_s)
+    int cs;              // TMA coordinate scale (2 for a stride-2 forward conv: the tensor map has elementStrides 2)
+    int dh0, dh_step, dw0, dw_step;       // input coordinate of tap (i, j): (oh0*cs + dh0 + i*dh_step, ow0*cs + dw0 + j*dw_step)
+    int w_r0, w_rstep, w_s0, w_sstep, KW; // packed-weight tap index = (w_r0 + i*w_rstep) * KW + (w_s0 + j*w_sstep)
     int tiles_h, tiles_w, n_blocks;
     long long total_tiles;
 };
@@ -108,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     const uint32_t tmem_base = *tmem_holder;
 
     const int cchunks = p.Cin_p / BLOCK_K;
-    const int num_kb = p.KH * p.KW * cchunks;
+    const int num_kb = p.n_r * p.n_s * cchunks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -123,10 +128,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                 t /= p.tiles_w;
                 const int th = static_cast<int>(t % p.tiles_h);
                 const int n = static_cast<int>(t / p.tiles_h);
-                const int h0 = th * TILE_H - p.pad, w0 = tw * TILE_W - p.pad;
+                const int h0 = th * TILE_H * p.cs + p.dh0, w0 = tw * TILE_W * p.cs + p.dw0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / cchunks, cc = kb - tap * cchunks;
-                    const int r = tap / p.KW, s = tap - r * p.KW;
+                    const int tapi = kb / cchunks, cc = kb - tapi * cchunks;
+                    const int ti = tapi / p.n_s, tj = tapi - ti * p.n_s;
+                    const int r = ti * p.dh_step, s = tj * p.dw_step;   // input offsets of this tap
+                    const int tap = (p.w_r0 + ti * p.w_rstep) * p.KW + (p.w_s0 + tj * p.w_sstep);
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -205,8 +212,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
             t /= p.tiles_w;
             const int th = static_cast<int>(t % p.tiles_h);
             const int n = static_cast<int>(t / p.tiles_h);
-            const int oh = th * TILE_H + lh, ow = tw * TILE_W + lw;
-            const bool valid = (oh < p.OH) && (ow < p.OW);
+            const int oh_l = th * TILE_H + lh, ow_l = tw * TILE_W + lw;
+            const bool valid = (oh_l < p.TOH) && (ow_l < p.TOW);
+            const int oh = oh_l * p.out_sh + p.out_oh, ow = ow_l * p.out_sw + p.out_ow;
             const size_t pix = static_cast<size_t>(n) * p.OH * p.OW + static_cast<size_t>(oh) * p.OW + ow;
             float* zrow = p.z + pix * p.z_ld + nblk * BLOCK_N;
             const float* arow = p.addend ? p.addend + pix * p.addend_ld + nblk * BLOCK_N : nullptr;
@@ -289,7 +297,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 4D NHWC bf16 activation map: dims {C, W, H, N}, box {64, TILE_W, TILE_H, 1}, 128B swizzle, zero fill.
 int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
-                  int box_h) {
+                  int box_h, int estride) {
     auto enc = get_encode_fn();
     if (!enc) {
         set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -297,8 +305,9 @@ int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // with elementStrides e the box spans box*e coordinates and transfers ceil(box*e / e) = box elements per dim
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUtensorMapSwizzle sw = box_c * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -339,7 +348,7 @@ int make_wgt_tmap(CUtensorMap* m, const void* base, int cols, int rows, int taps
 }
 
 bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
-    return stride == 1 && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH >= 1 && KW >= 1 && KH <= 9 && KW <= 9;
+    return (stride == 1 || stride == 2) && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH >= 1 && KW >= 1 && KH <= 9 && KW <= 9;
 }
 
 template <int BLOCK_N, bool SPLIT>
@@ -358,52 +367,90 @@ static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const 
     return FCD_OK;
 }
 
-int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
-                  const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W,
-                  int Cin_p, int Cout_p, int KH, int KW, int pad, double* stat_sum, double* stat_sqsum,
-                  cudaStream_t stream) {
-    const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
-    FCD_CHECK_ARG(OH > 0 && OW > 0, "conv2d_fwd_tc: empty output");
-    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0 && addend_ld % 4 == 0, "conv2d_fwd_tc: pitches must keep 16-byte alignment");
+static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
+                       int w_rows, int w_cols, int w_taps, ConvTcParams p, int N, int cs, cudaStream_t stream) {
     const bool split = (x_lo != nullptr) && (w_lo != nullptr);
-    const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
-
+    const int block_n = (p.Cout_p % 128 == 0) ? 128 : 64;
     CUtensorMap mxh, mxl, mwh, mwl;
     int rc;
-    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, BLOCK_K, TILE_W, TILE_H))) return rc;
-    if ((rc = make_wgt_tmap(&mwh, w_hi, Cin_p, Cout_p, KH * KW, BLOCK_K, block_n))) return rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, cs))) return rc;
+    if ((rc = make_wgt_tmap(&mwh, w_hi, w_cols, w_rows, w_taps, BLOCK_K, block_n))) return rc;
     if (split) {
-        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, BLOCK_K, TILE_W, TILE_H))) return rc;
-        if ((rc = make_wgt_tmap(&mwl, w_lo, Cin_p, Cout_p, KH * KW, BLOCK_K, block_n))) return rc;
+        if ((rc = make_act_tmap(&mxl, x_lo, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, cs))) return rc;
+        if ((rc = make_wgt_tmap(&mwl, w_lo, w_cols, w_rows, w_taps, BLOCK_K, block_n))) return rc;
     } else {
         mxl = mxh;
         mwl = mwh;
     }
-    ConvTcParams p;
-    p.bias = bias;
-    p.addend = addend;
-    p.addend_ld = addend_ld;
-    p.z = z;
-    p.stat_sum = stat_sum;
-    p.stat_sqsum = stat_sqsum;
-    p.z_ld = z_ld;
     p.N = N;
-    p.OH = OH;
-    p.OW = OW;
-    p.Cin_p = Cin_p;
-    p.Cout_p = Cout_p;
-    p.KH = KH;
-    p.KW = KW;
-    p.pad = pad;
-    p.tiles_h = ceil_div(OH, TILE_H);
-    p.tiles_w = ceil_div(OW, TILE_W);
-    p.n_blocks = Cout_p / block_n;
+    p.cs = cs;
+    p.tiles_h = ceil_div(p.TOH, TILE_H);
+    p.tiles_w = ceil_div(p.TOW, TILE_W);
+    p.n_blocks = p.Cout_p / block_n;
     p.total_tiles = 1LL * N * p.tiles_h * p.tiles_w * p.n_blocks;
     if (block_n == 128)
         return split ? launch_conv_tc<128, true>(mxh, mxl, mwh, mwl, p, stream)
                      : launch_conv_tc<128, false>(mxh, mxl, mwh, mwl, p, stream);
     return split ? launch_conv_tc<64, true>(mxh, mxl, mwh, mwl, p, stream)
                  : launch_conv_tc<64, false>(mxh, mxl, mwh, mwl, p, stream);
+}
+
+int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,
+                  const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int H, int W,
+                  int Cin_p, int Cout_p, int KH, int KW, int stride, int pad, double* stat_sum, double* stat_sqsum,
+                  cudaStream_t stream) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+    FCD_CHECK_ARG(OH > 0 && OW > 0, "conv2d_fwd_tc: empty output");
+    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0 && addend_ld % 4 == 0, "conv2d_fwd_tc: pitches must keep 16-byte alignment");
+    ConvTcParams p{};
+    p.bias = bias; p.addend = addend; p.addend_ld = addend_ld; p.z = z;
+    p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum; p.z_ld = z_ld;
+    p.OH = OH; p.OW = OW; p.TOH = OH; p.TOW = OW;
+    p.out_sh = 1; p.out_oh = 0; p.out_sw = 1; p.out_ow = 0;
+    p.Cin_p = Cin_p; p.Cout_p = Cout_p;
+    p.n_r = KH; p.n_s = KW;
+    p.dh0 = -pad; p.dh_step = 1; p.dw0 = -pad; p.dw_step = 1;
+    p.w_r0 = 0; p.w_rstep = 1; p.w_s0 = 0; p.w_sstep = 1; p.KW = KW;
+    return run_conv_tc(x_hi, x_lo, x_ld, H, W, w_hi, w_lo, Cout_p, Cin_p, KH * KW, p, N, stride, stream);
+}
+
+// Stride-2 dgrad on the tcgen05 engine: the input-gradient pixels split into stride*stride parity classes; each class
+// is a stride-1 implicit GEMM over dz with the subset of taps whose parity matches, scattered to every stride-th pixel.
+//   dx[n, h, w, ci] = sum_{r,s: (h+pad-r), (w+pad-s) divisible by stride} dz[n, (h+pad-r)/stride, (w+pad-s)/stride, :] . w[r,s][:, ci]
+// wT are MODE-1 packed weights: wT[(KH-1-r)*KW + (KW-1-s)][ci][co].
+int conv2d_dgrad_strided_tc(const void* dz_hi, const void* dz_lo, int dz_ld, const void* wT_hi, const void* wT_lo,
+                            const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p,
+                            int Cout_p, int KH, int KW, int stride, int pad, cudaStream_t stream) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;   // dz dims
+    FCD_CHECK_ARG(dx_ld % 4 == 0 && dz_ld % 8 == 0 && addend_ld % 4 == 0, "conv2d_dgrad_strided_tc: pitches");
+    for (int ph = 0; ph < stride; ++ph) {
+        for (int pw = 0; pw < stride; ++pw) {
+            const int r0 = (ph + pad) % stride, s0 = (pw + pad) % stride;
+            const int n_r = r0 < KH ? (KH - r0 + stride - 1) / stride : 0;
+            const int n_s = s0 < KW ? (KW - s0 + stride - 1) / stride : 0;
+            const int TOH = (H - ph + stride - 1) / stride, TOW = (W - pw + stride - 1) / stride;
+            if (TOH <= 0 || TOW <= 0) continue;
+            if (n_r == 0 || n_s == 0) {
+                set_error(FCD_ERR_UNSUPPORTED, "conv2d_dgrad_strided_tc: a parity class has no taps (K=%dx%d stride %d)", KH, KW, stride);
+                return FCD_ERR_UNSUPPORTED;
+            }
+            ConvTcParams p{};
+            p.bias = nullptr; p.addend = addend; p.addend_ld = addend_ld; p.z = dx;
+            p.stat_sum = nullptr; p.stat_sqsum = nullptr; p.z_ld = dx_ld;
+            p.OH = H; p.OW = W; p.TOH = TOH; p.TOW = TOW;
+            p.out_sh = stride; p.out_oh = ph; p.out_sw = stride; p.out_ow = pw;
+            p.Cin_p = Cout_p;   // K side = dz channels
+            p.Cout_p = Cin_p;   // N side = dx channels
+            p.n_r = n_r; p.n_s = n_s;
+            // tap i <-> r = r0 + i*stride reads dz row  (h + pad - r)/stride = oh_l + (ph + pad - r0)/stride - i
+            p.dh0 = (ph + pad - r0) / stride; p.dh_step = -1;
+            p.dw0 = (pw + pad - s0) / stride; p.dw_step = -1;
+            p.w_r0 = KH - 1 - r0; p.w_rstep = -stride; p.w_s0 = KW - 1 - s0; p.w_sstep = -stride; p.KW = KW;
+            int rc = run_conv_tc(dz_hi, dz_lo, dz_ld, OH, OW, wT_hi, wT_lo, Cin_p, Cout_p, KH * KW, p, N, 1, stream);
+            if (rc) return rc;
+        }
+    }
+    return FCD_OK;
 }
 
 }  // namespace fcd

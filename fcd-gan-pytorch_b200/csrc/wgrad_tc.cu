@@ -18,7 +18,7 @@ namespace fcd {
 using namespace tc;
 
 int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
-                  int box_h);
+                  int box_h, int estride);
 
 namespace {
 
@@ -41,7 +41,7 @@ struct WCfg {
 struct WgradParams {
     float* ws;            // [R*64][Cout_p] fp32, zero-initialised by the host wrapper
     int N, OH, OW;
-    int Cin_p, Cout_p, KH, KW, pad;
+    int Cin_p, Cout_p, KH, KW, pad, stride;
     int cchunks, R;       // row groups = taps * cchunks
     int m_blocks, n_blocks, ksplit;
     int tiles_h, tiles_w;
@@ -110,11 +110,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const int r = tapv[sub] / p.KW, s = tapv[sub] % p.KW;
-                    tma_load_4d(st + sub * SUB_BYTES, &map_x_hi, &full_bar[stage], cbv[sub] * 64, w0 + s - p.pad,
-                                h0 + r - p.pad, n);
+                    // stride 2: the x tensor map has elementStrides 2, so the box picks every other pixel
+                    const int xw = w0 * p.stride + s - p.pad, xh = h0 * p.stride + r - p.pad;
+                    tma_load_4d(st + sub * SUB_BYTES, &map_x_hi, &full_bar[stage], cbv[sub] * 64, xw, xh, n);
                     if (SPLIT)
-                        tma_load_4d(st + C::A_BYTES + sub * SUB_BYTES, &map_x_lo, &full_bar[stage], cbv[sub] * 64,
-                                    w0 + s - p.pad, h0 + r - p.pad, n);
+                        tma_load_4d(st + C::A_BYTES + sub * SUB_BYTES, &map_x_lo, &full_bar[stage], cbv[sub] * 64, xw, xh, n);
                 }
                 uint8_t* sb = st + C::A_BYTES * C::PLANES;
 #pragma unroll
@@ -231,7 +231,7 @@ __global__ void channel_sum_kernel2(SplitCPtr v, int ld, long long npix, int C, 
 }  // namespace
 
 bool wgrad_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
-    return stride == 1 && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH <= 9 && KW <= 9;
+    return (stride == 1 || stride == 2) && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH <= 9 && KW <= 9;
 }
 
 size_t wgrad_tc_workspace(int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int pad) {
@@ -268,9 +268,9 @@ static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CU
 }
 
 int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz_hi, const void* dz_lo, int dz_ld,
-                    float* dw, int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH, int KW, int pad,
-                    int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
+                    float* dw, int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH, int KW, int stride,
+                    int pad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
     const size_t need = wgrad_tc_workspace(N, H, W, Cin_p, Cout_p, KH, KW, pad);
     FCD_CHECK_ARG(workspace && workspace_bytes >= need, "conv2d_wgrad_tc: workspace too small (%zu < %zu)",
                   workspace_bytes, need);
@@ -280,7 +280,7 @@ int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz
     WgradParams p;
     p.ws = static_cast<float*>(workspace);
     p.N = N; p.OH = OH; p.OW = OW;
-    p.Cin_p = Cin_p; p.Cout_p = Cout_p; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.Cin_p = Cin_p; p.Cout_p = Cout_p; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
     p.cchunks = Cin_p / 64;
     p.R = KH * KW * p.cchunks;
     p.m_blocks = (p.R + 1) / 2;
@@ -297,11 +297,11 @@ int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz
 
     CUtensorMap mxh, mxl, mgh, mgl;
     int rc;
-    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H))) return rc;
-    if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H))) return rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H, stride))) return rc;
+    if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H, 1))) return rc;
     if (split) {
-        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H))) return rc;
-        if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H))) return rc;
+        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H, stride))) return rc;
+        if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H, 1))) return rc;
     } else {
         mxl = mxh;
         mgl = mgh;

@@ -295,7 +295,7 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     """nn.Conv2d forward (Module.py:26-216) + recorded wgrad/dgrad."""
     Cout, Cin, KH, KW = w.shape
     assert Cin == x.C, f"conv: weight expects {Cin} channels, activation has {x.C}"
-    Cout_p, Cin_p = pad_ch(Cout, stride == 1), x.Cp
+    Cout_p, Cin_p = pad_ch(Cout), x.Cp
     N, H, W = x.N, x.H, x.W
     OH = (H + 2 * pad - KH) // stride + 1
     OW = (W + 2 * pad - KW) // stride + 1
@@ -339,9 +339,11 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
                       x.ld, g.data_ptr(), x.ld, N, OH, OW, Cout_p, Cin_p, KH, KW, 1, KH - 1 - pad, None, None,
                       _cfg["engine"], tag=f"conv_dgrad_{_conv_engine_name(Cout_p, Cin_p, KH, KW, 1)} {shape}", flops=flops)
             else:
-                _call("fcd_conv2d_dgrad_strided", dz.p_hi(), dz.p_lo(), dz.ld, w_hi.data_ptr(), _lib.ptr(w_lo), addend,
-                      x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW, stride, pad,
-                      tag=f"conv_dgrad_simt {shape}", flops=flops)
+                wd_hi, wd_lo = _packed(w, Cout_p, Cin_p, 1, wtag)
+                deng = _conv_engine_name(Cout_p, Cin_p, KH, KW, stride)
+                _call("fcd_conv2d_dgrad_strided", dz.p_hi(), dz.p_lo(), dz.ld, w_hi.data_ptr(), _lib.ptr(w_lo),
+                      wd_hi.data_ptr(), _lib.ptr(wd_lo), addend, x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW,
+                      stride, pad, _cfg["engine"], tag=f"conv_dgrad_{deng} {shape}", flops=flops)
             x.mark_ready()
         z.dz = None
 

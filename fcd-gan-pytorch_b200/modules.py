@@ -331,8 +331,8 @@ class Discriminator_SRGAN_simple(nn.Module):
 
         def fn(tape, inputs, need):
             training = self.training
-            a = E.stage_input(tape, inputs[0], need[0], tc=False)     # stride-2 layers run on the SIMT engine
-            b = E.stage_input(tape, inputs[1], need[1], tc=False)
+            a = E.stage_input(tape, inputs[0], need[0])
+            b = E.stage_input(tape, inputs[1], need[1])
             fx = self._features(tape, a, training, need[0])
             fy = self._features(tape, b, training, need[1])
             c1, c3 = self.classifier[1], self.classifier[3]

@@ -73,11 +73,14 @@ int fcd_conv2d_fwd(const void* x_hi, const void* x_lo, int x_ld, const void* w_h
                    int KW, int stride, int pad, double* stat_sum, double* stat_sqsum, int engine, void* stream);
 
 /* dgrad for stride-2 convolutions (Module.py:196-207 backward w.r.t. the input):
- * dx[n,h,w,ci] = sum_{r,s,co : (h+pad-r)%2==0,...} dz[n,(h+pad-r)/2,(w+pad-s)/2,co] * w[r*KW+s][co][ci]
- * w are the FORWARD (mode 0) packed weights. */
+ * dx[n,h,w,ci] = sum_{r,s : (h+pad-r)%stride==0,...} dz[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[r][s][co][ci]
+ * w = FORWARD (mode 0) packed weights (SIMT engine), wT = mode-1 packed weights (tcgen05 engine: the input pixels are
+ * split into stride x stride parity classes, each a stride-1 implicit GEMM over its subset of taps).  Either may be
+ * NULL; engine AUTO prefers tcgen05 when wT is given and the channel counts are multiples of 64. */
 int fcd_conv2d_dgrad_strided(const void* dz_hi, const void* dz_lo, int dz_ld, const void* w_hi, const void* w_lo,
-                             const float* addend, int addend_ld, float* dx, int dx_ld, int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW,
-                             int stride, int pad, void* stream);
+                             const void* wT_hi, const void* wT_lo, const float* addend, int addend_ld, float* dx, int dx_ld,
+                             int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int stride, int pad, int engine,
+                             void* stream);
 
 /* wgrad (nn.Conv2d backward w.r.t. weight and bias):
  * dw[co][ci][r][s] (+)= sum_{n,oh,ow} dz[n,oh,ow,co] * x[n,oh*stride+r-pad,ow*stride+s-pad,ci]   (OIHW fp32,
