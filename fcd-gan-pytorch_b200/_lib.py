@@ -78,12 +78,17 @@ def load():
     return lib
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args):
     """Call an int-returning entry point and raise FcdError with the library's message on failure."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise FcdError(f"{name} -> {rc}: {lib.fcd_last_error().decode(errors='replace')}")
+        raise FcdError(f"{name} -> {rc}: {load().fcd_last_error().decode(errors='replace')}")
     return rc
 
 

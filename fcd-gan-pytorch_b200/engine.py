@@ -52,14 +52,19 @@ def set_engine(engine: int) -> None:
 PROFILE = None       # set to a list: every C-ABI call is bracketed by CUDA events -> (name, tag, flops, bytes, e0, e1)
 
 
+def _raw_stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the capture stream under CUDA-graph capture)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
 def _call(name, *args, tag=None, flops=0.0, nbytes=0.0):
     global launch_count
     launch_count += 1
     if PROFILE is None:
-        return _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+        return _lib.call(name, *args, _raw_stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    rc = _lib.call(name, *args, torch.cuda.current_stream().cuda_stream)
+    rc = _lib.call(name, *args, _raw_stream())
     e1.record()
     PROFILE.append((name, tag or name, flops, nbytes, e0, e1))
     return rc
@@ -154,10 +159,22 @@ class Z:
 
 # --------------------------------------------------------------------------------------------------
 _workspace: Dict[torch.device, torch.Tensor] = {}
+_weight_epoch = 0     # bumped whenever parameters may have changed WITHOUT their version counter moving (graph replay)
 
 
 def clear_caches():
     _workspace.clear()
+
+
+def bump_weight_epoch() -> None:
+    """Invalidate every cached packed weight.  A CUDA-graph replay updates parameters on the device without
+    touching `Tensor._version`, so `graph.GraphedStep` calls this after each replay."""
+    global _weight_epoch
+    _weight_epoch += 1
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_current_stream_capturing()
 
 
 def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
@@ -172,8 +189,9 @@ def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
         except AttributeError:
             pass
     key = (mode, _cfg["split"], Cout_p, Cin_p, tag)
-    stamp = (w.data_ptr(), w._version)
-    ent = cache.get(key)
+    stamp = (w.data_ptr(), w._version, _weight_epoch)
+    capturing = _capturing()      # under graph capture always re-pack (the packing kernel must be part of the graph)
+    ent = None if capturing else cache.get(key)
     if ent is not None and ent[0] == stamp:
         return ent[1], ent[2]
     Cout, Cin, KH, KW = w.shape
@@ -181,11 +199,14 @@ def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
     hi = torch.empty((KH * KW, rows, cols), dtype=torch.bfloat16, device=w.device)
     lo = torch.empty_like(hi) if _cfg["split"] else None
     _call("fcd_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, Cout_p, Cin_p, mode, hi.data_ptr(), _lib.ptr(lo))
-    cache[key] = (stamp, hi, lo)
+    if not capturing:
+        cache[key] = (stamp, hi, lo)
     return hi, lo
 
 
 def _ws(device, nbytes: int) -> torch.Tensor:
+    if _capturing():              # graph-private memory must not leak into the eager cache
+        return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
     cur = _workspace.get(device)
     if cur is None or cur.numel() < nbytes:
         cur = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

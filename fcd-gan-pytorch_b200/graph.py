@@ -1,0 +1,49 @@
+"""CUDA-graph capture of a whole training iteration.
+
+A network pass here is a few hundred short C-ABI launches issued from Python; at B200 speeds the host needs longer
+to ISSUE an iteration (~30 ms for Generator + Discriminator) than the GPU needs to run it.  Capturing the iteration
+(forward, hand-written backward, optimizer steps — everything is stream-ordered and allocation goes through torch's
+graph-private pool) into one CUDA graph removes that bound: a replay is a single launch.
+
+    step = GraphedStep(fn, static_inputs)      # fn(*static_inputs) -> tensors; runs warm-up iterations, then captures
+    out = step()                               # replay; `out` are the static output tensors
+    step.copy_inputs(*new_inputs)              # refill the static input buffers (e.g. from pinned host memory)
+
+Requirements (the usual CUDA-graph rules): shapes fixed; optimizers constructed with `capturable=True`;
+`zero_grad(set_to_none=True)` inside `fn`; no host synchronisation inside `fn`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from . import engine as E
+
+
+class GraphedStep:
+    def __init__(self, fn: Callable, static_inputs: Sequence[torch.Tensor], warmup: int = 3):
+        self.fn = fn
+        self.static_inputs = list(static_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = E.launch_count
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.static_inputs)
+        self.launches_per_replay = E.launch_count - n0      # libfcd_b200 C-ABI calls recorded in the graph
+        E.bump_weight_epoch()
+
+    def copy_inputs(self, *tensors: torch.Tensor) -> None:
+        for dst, src in zip(self.static_inputs, tensors):
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self):
+        self.graph.replay()
+        E.bump_weight_epoch()      # parameters changed on the device without their version counters moving
+        return self.outputs
