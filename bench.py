@@ -133,6 +133,7 @@ def run_ours(args):
     torch.manual_seed(0)
     netG, netD = fb.Generator(C).to(dev).train(), fb.Discriminator_SRGAN_simple(C).to(dev).train()
     P.broadcast_parameters([netG, netD])
+    # world > 1 stays eager: capturing the NCCL all-reduces hung on this stack (torch 2.11 / NCCL 2.28.9), see DESIGN.md §7
     use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
     optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=use_graph)   # Demo_USSS.py:121
     optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=use_graph)                   # Demo_RSSS.py:157
@@ -238,14 +239,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (t.item() / 1e3)
 
+    # ---- instrumented pass: per-call CUDA events -> dominant kernel roofline (not part of the timed numbers).
+    # Every rank runs it (the step contains collectives when world > 1); only rank 0 records events.
+    nprof = min(args.steps, 3)
+    if rank == 0:
+        E.PROFILE = []
+    for _ in range(nprof):
+        eager_step(*data)
+    barrier()
     out = None
     if rank == 0:
-        # ---- instrumented pass: per-call CUDA events -> dominant kernel roofline (not part of the timed numbers)
-        E.PROFILE = []
-        nprof = min(args.steps, 3)
-        for _ in range(nprof):
-            eager_step(*data)
-        torch.cuda.synchronize()
         agg = {}
         for name, tag, flops, nbytes, a, b in E.PROFILE:
             d = agg.setdefault(tag, [0.0, 0, 0.0, name])

@@ -263,7 +263,8 @@ class Tape:
             a.reset_grad()
         self.pgrads = {}
         for fn in reversed(self.ops):
-            fn()
+            fn(self)         # the tape is passed in (closures must not capture it: tape <-> closure cycles would
+                             # keep a whole iteration's device buffers alive until Python's cyclic GC runs)
         for a in self.acts:      # gradient buffers are per replay
             a.reset_grad()
         return self.pgrads
@@ -294,7 +295,7 @@ def act_to_nchw(tape: Tape, a: Act, grad_slot: dict) -> torch.Tensor:
     out = torch.empty((a.N, a.C, a.H, a.W), dtype=torch.float32, device=tape.device)
     _call("fcd_unstage_split_to_nchw", a.p_hi(), a.p_lo(), a.ld, a.N, a.C, a.H, a.W, out.data_ptr())
 
-    def backward():
+    def backward(tape):
         dout = grad_slot["dout"].contiguous()
         assert not a.ready
         _call("fcd_stage_nchw_to_f32", dout.data_ptr(), a.N, a.C, a.H, a.W, a.grad.data_ptr(), a.ld, a.Cp)
@@ -338,7 +339,7 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     if stats and not fuse:
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
 
-    def backward():
+    def backward(tape):
         dz = z.dz
         assert dz is not None, "conv backward: output gradient missing"
         gw, acc = tape.pgrad(w)
@@ -406,7 +407,7 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
           None if residual is None else residual.p_hi(), None if residual is None else residual.p_lo(),
           0 if residual is None else residual.ld, out.p_hi(), out.p_lo(), out.ld, npix, Cp)
 
-    def backward():
+    def backward(tape):
         assert out.ready, f"bn_act backward: gradient of {out.name} missing"
         da = out.grad
         dz = Act.empty(z.N, z.H, z.W, C, dev, Cp)
@@ -458,7 +459,7 @@ def maxpool2(tape: Tape, x: Act) -> Act:
     out = tape.new_act(x.N, x.H // 2, x.W // 2, x.C, x.Cp)
     _call("fcd_maxpool2_fwd", x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp, out.p_hi(), out.p_lo(), out.ld)
 
-    def backward():
+    def backward(tape):
         assert out.ready
         g = x.grad
         _call("fcd_maxpool2_bwd", out.grad.data_ptr(), out.ld, x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp,
@@ -477,7 +478,7 @@ def upsample2x_into(tape: Tape, x: Act, dst: Act) -> None:
     _call("fcd_upsample2x_bilinear_fwd", x.p_hi(), x.p_lo(), x.ld, x.N, x.H, x.W, x.Cp, dst.p_hi(), dst.p_lo(), dst.ld,
           dst.H, dst.W, pt, pl)
 
-    def backward():
+    def backward(tape):
         assert dst.ready and not x.ready
         _call("fcd_upsample2x_bilinear_bwd", dst.grad.data_ptr(), dst.ld, x.N, x.H, x.W, x.Cp, dst.H, dst.W, pt, pl,
               x.grad.data_ptr(), x.ld)
@@ -511,7 +512,7 @@ def conv_transpose2x2_into(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor,
           dst.p_lo(), dst.ld, dst.H, dst.W, pt, pl)
     del planes
 
-    def backward():
+    def backward(tape):
         assert dst.ready and not x.ready
         dev = tape.device
         g_hi = torch.empty((4, N, h, wd, Cout_p), dtype=torch.bfloat16, device=dev)
@@ -558,8 +559,10 @@ def outconv_sigmoid(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, grad_s
     w2 = w.reshape(n_out, Cin)
     _call("fcd_outconv_sigmoid_fwd", x.p_hi(), x.p_lo(), x.ld, Cin, w2.data_ptr(), b.data_ptr(), n_out, x.N, x.H, x.W,
           out.data_ptr())
+    result, out = out, out.detach()   # the closure keeps a grad_fn-free alias: capturing the RETURNED tensor would close
+                                      # the cycle output -> grad_fn -> tape -> closure -> output and defer freeing to the GC
 
-    def backward():
+    def backward(tape):
         dout = grad_slot["dout"].contiguous()
         gw, acc = tape.pgrad(w)
         gb, _ = tape.pgrad(b)
@@ -570,7 +573,7 @@ def outconv_sigmoid(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, grad_s
         x.mark_ready()
 
     tape.push(backward)
-    return out
+    return result
 
 
 def disc_head(tape: Tape, fx: Act, fy: Act, w1, b1, w2, b2, grad_slot: dict) -> torch.Tensor:
@@ -586,8 +589,9 @@ def disc_head(tape: Tape, fx: Act, fy: Act, w1, b1, w2, b2, grad_slot: dict) -> 
     _call("fcd_fc_fwd", pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), N, C, O1, 3, pre1.data_ptr(), h1.data_ptr())
     out = torch.empty((N,), dtype=torch.float32, device=dev)
     _call("fcd_fc_fwd", h1.data_ptr(), w2.data_ptr(), b2.data_ptr(), N, O1, 1, 4, None, out.data_ptr())
+    result, out = out, out.detach()   # see outconv_sigmoid: no reference cycle through the returned tensor
 
-    def backward():
+    def backward(tape):
         dout = grad_slot["dout"].contiguous()
         gw2, a2 = tape.pgrad(w2)
         gb2, _ = tape.pgrad(b2)
@@ -607,7 +611,7 @@ def disc_head(tape: Tape, fx: Act, fy: Act, w1, b1, w2, b2, grad_slot: dict) -> 
         fy.mark_ready()
 
     tape.push(backward)
-    return out
+    return result
 
 
 def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:
@@ -615,7 +619,7 @@ def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:
     out = torch.empty((z.N, z.C, z.H, z.W), dtype=torch.float32, device=tape.device)
     _call("fcd_unstage_f32_to_nchw", z.t.data_ptr(), z.ld, z.N, z.C, z.H, z.W, out.data_ptr(), 0)
 
-    def backward():
+    def backward(tape):
         dout = grad_slot["dout"].contiguous()
         dz = Act.empty(z.N, z.H, z.W, z.C, tape.device, z.Cp)
         _call("fcd_stage_nchw_to_split", dout.data_ptr(), None, z.N, z.C, z.H, z.W, dz.p_hi(), dz.p_lo(), dz.ld, dz.Cp)
@@ -669,7 +673,7 @@ class NetFunction(torch.autograd.Function):
         # input gradients must be extracted before Tape.run() resets the gradient buffers -> do it as a final op
         results = {}
 
-        def grab():
+        def grab(_tape):
             for i, a in enumerate(ctx.input_acts):
                 if need_in[i]:
                     results[i] = unstage_grad(a)

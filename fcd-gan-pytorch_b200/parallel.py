@@ -23,8 +23,11 @@ def init_from_env(backend: Optional[str] = None) -> int:
     import os
 
     if not dist.is_initialized():
+        import datetime
+
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        dist.init_process_group(backend=backend)
+        # a mismatched collective should fail in minutes, not hold a GPU box for the default 10
+        dist.init_process_group(backend=backend, timeout=datetime.timedelta(seconds=int(os.environ.get("FCD_DIST_TIMEOUT_S", "180"))))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if torch.cuda.is_available():
         torch.cuda.set_device(local)

@@ -220,7 +220,7 @@ def test_bn_act_fwd_bwd(act, use_bn, training, residual):
     dr = torch.randn(N, C, H, W, device=DEV)
     out.grad.copy_(dr.permute(0, 2, 3, 1))
     out.mark_ready()
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     wants = [zr] + ([g64, b64] if use_bn else []) + ([s64] if act == E.ACT_PRELU else []) + ([rres] if residual else [])
     grads = torch.autograd.grad(r, wants, dr.double())
     dz_ref = grads[0]
@@ -251,7 +251,7 @@ def test_maxpool(H, W):
     d = torch.randn_like(ref)
     out.grad.copy_(d.permute(0, 2, 3, 1).float())
     out.mark_ready()
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     (gx,) = torch.autograd.grad(ref, xr, d)
     assert rel(a.grad.permute(0, 3, 1, 2), gx) < 1e-6
 
@@ -276,7 +276,7 @@ def test_upsample_into_concat(h, w, H, W):
     d = torch.randn(N, H, W, 192, device=DEV)
     cat.grad.copy_(d)
     cat.mark_ready()
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     (gx,) = torch.autograd.grad(ref, xr, d[..., 128:192].permute(0, 3, 1, 2).double())
     assert rel(a.grad.permute(0, 3, 1, 2), gx) < 1e-5
 
@@ -303,7 +303,7 @@ def test_conv_transpose_into_concat():
     d = torch.randn(N, H, W, 128, device=DEV)
     cat.grad.copy_(d)
     cat.mark_ready()
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     gx, gw, gb = torch.autograd.grad(ref, (xr, w64, b64), d[..., 64:].permute(0, 3, 1, 2).double())
     assert rel(a.grad.permute(0, 3, 1, 2), gx) < 3e-5
     assert rel(tape.pgrads[id(wt)], gw) < 3e-5 and rel(tape.pgrads[id(b)], gb) < 3e-5
@@ -326,7 +326,7 @@ def test_outconv_sigmoid():
     assert rel(out, ref) < 1e-5
     d = torch.randn_like(out)
     slot["dout"] = d
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     gx, gw, gb = torch.autograd.grad(ref, (xr, w64, b64), d.double())
     assert rel(a.grad.permute(0, 3, 1, 2), gx) < 1e-5
     assert rel(tape.pgrads[id(w)], gw) < 1e-5 and rel(tape.pgrads[id(b)], gb) < 1e-5
@@ -353,7 +353,7 @@ def test_disc_head():
     assert out.shape == (N,) and rel(out, ref) < 2e-5
     d = torch.randn(N, device=DEV)
     slot["dout"] = d
-    tape.ops[-1]()
+    tape.ops[-1](tape)
     g = torch.autograd.grad(ref, [xr, yr] + P, d.double())
     assert rel(ax.grad.permute(0, 3, 1, 2), g[0]) < 2e-5 and rel(ay.grad.permute(0, 3, 1, 2), g[1]) < 2e-5
     for p, gr in zip((w1, b1, w2, b2), g[2:]):
