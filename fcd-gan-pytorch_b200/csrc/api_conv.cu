@@ -42,6 +42,10 @@ bool wgrad_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);
 size_t wgrad_tc_workspace(int N, int H, int W, int Cin_p, int Cout_p, int KH, int KW, int pad);
 int conv2d_wgrad_tc(const void*, const void*, int, const void*, const void*, int, float*, int, int, int, int, int, int,
                     int, int, int, int, int, int, void*, size_t, cudaStream_t);
+int conv2d_taps_tc(const void*, const void*, int, int, int, const void*, const void*, const float*, const float*, int, float*,
+                   int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv2d_taps_wgrad_tc(const void*, const void*, int, int, int, const void*, const void*, int, int, int, float*, int, int, int,
+                         int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream);
 
@@ -132,6 +136,31 @@ int fcd_conv2d_wgrad(const void* x_hi, const void* x_lo, int x_ld, const void* d
     }
     return conv2d_wgrad_simt(x_hi, x_lo, x_ld, dz_hi, dz_lo, dz_ld, dw_oihw, db, N, H, W, Cin, Cin_p, Cout, Cout_p, KH,
                              KW, stride, pad, accumulate, as_stream(stream));
+}
+
+int fcd_conv2d_taps_fwd(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
+                        const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int OH, int OW,
+                        int Cin_p, int Cout_p, int n_r, int n_s, int dh0, int dh_step, int dw0, int dw_step, int csh, int csw,
+                        void* stream) {
+    FCD_CHECK_ARG(x_hi && w_hi && z, "fcd_conv2d_taps_fwd: null pointer");
+    return conv2d_taps_tc(x_hi, x_lo, x_ld, XH, XW, w_hi, w_lo, bias, addend, addend_ld, z, z_ld, N, OH, OW, Cin_p, Cout_p, n_r,
+                          n_s, dh0, dh_step, dw0, dw_step, csh, csw, as_stream(stream));
+}
+
+size_t fcd_conv2d_taps_wgrad_workspace(int Cin_p, int Cout_p, int n_r, int n_s) {
+    return sizeof(float) * static_cast<size_t>(n_r) * n_s * Cin_p * Cout_p;
+}
+
+int fcd_conv2d_taps_wgrad(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* dz_hi, const void* dz_lo,
+                          int dz_ld, int GH, int GW, float* dw, float* db, int N, int Cin, int Cin_p, int Cout, int Cout_p,
+                          int n_r, int n_s, int dh0, int dw0, int dw_step, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    FCD_CHECK_ARG(x_hi && dz_hi && dw, "fcd_conv2d_taps_wgrad: null pointer");
+    int rc = conv2d_taps_wgrad_tc(x_hi, x_lo, x_ld, XH, XW, dz_hi, dz_lo, dz_ld, GH, GW, dw, N, Cin, Cin_p, Cout, Cout_p, n_r, n_s,
+                                  dh0, dw0, dw_step, accumulate, workspace, workspace_bytes, as_stream(stream));
+    if (rc) return rc;
+    if (db) return channel_sum_split(dz_hi, dz_lo, dz_ld, 1LL * N * GH * GW, Cout, db, accumulate, as_stream(stream));
+    return FCD_OK;
 }
 
 }  // extern "C"

@@ -60,7 +60,7 @@ struct ConvTcParams {
     int out_sh, out_oh, out_sw, out_ow;   // output pixel = (oh * out_sh + out_oh, ow * out_sw + out_ow)
     int Cin_p, Cout_p;
     int n_r, n_s;        // taps iterated in this launch: i in [0, n_r), j in [0, n_s)
-    int cs;              // TMA coordinate scale (2 for a stride-2 forward conv: the tensor map has elementStrides 2)
+    int csh, csw;        // TMA coordinate scale per dim (2 for a stride-2 forward conv: the tensor map has elementStrides 2)
     int dh0, dh_step, dw0, dw_step;       // input coordinate of tap (i, j): (oh0*cs + dh0 + i*dh_step, ow0*cs + dw0 + j*dw_step)
     int w_r0, w_rstep, w_s0, w_sstep, KW; // packed-weight tap index = (w_r0 + i*w_rstep) * KW + (w_s0 + j*w_sstep)
     int tiles_h, tiles_w, n_blocks;
@@ -128,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                 t /= p.tiles_w;
                 const int th = static_cast<int>(t % p.tiles_h);
                 const int n = static_cast<int>(t / p.tiles_h);
-                const int h0 = th * TILE_H * p.cs + p.dh0, w0 = tw * TILE_W * p.cs + p.dw0;
+                const int h0 = th * TILE_H * p.csh + p.dh0, w0 = tw * TILE_W * p.csw + p.dw0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tapi = kb / cchunks, cc = kb - tapi * cchunks;
                     const int ti = tapi / p.n_s, tj = tapi - ti * p.n_s;
@@ -297,7 +297,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 4D NHWC bf16 activation map: dims {C, W, H, N}, box {64, TILE_W, TILE_H, 1}, 128B swizzle, zero fill.
 int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
-                  int box_h, int estride) {
+                  int box_h, int estride_w, int estride_h) {
     auto enc = get_encode_fn();
     if (!enc) {
         set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -306,8 +306,8 @@ int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
     // with elementStrides e the box spans box*e coordinates and transfers ceil(box*e / e) = box elements per dim
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride_w), (cuuint32_t)(box_h * estride_h), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride_w, (cuuint32_t)estride_h, 1};
     CUtensorMapSwizzle sw = box_c * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -368,22 +368,23 @@ static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const 
 }
 
 static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
-                       int w_rows, int w_cols, int w_taps, ConvTcParams p, int N, int cs, cudaStream_t stream) {
+                       int w_rows, int w_cols, int w_taps, ConvTcParams p, int N, int csh, int csw, cudaStream_t stream) {
     const bool split = (x_lo != nullptr) && (w_lo != nullptr);
     const int block_n = (p.Cout_p % 128 == 0) ? 128 : 64;
     CUtensorMap mxh, mxl, mwh, mwl;
     int rc;
-    if ((rc = make_act_tmap(&mxh, x_hi, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, cs))) return rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, csw, csh))) return rc;
     if ((rc = make_wgt_tmap(&mwh, w_hi, w_cols, w_rows, w_taps, BLOCK_K, block_n))) return rc;
     if (split) {
-        if ((rc = make_act_tmap(&mxl, x_lo, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, cs))) return rc;
+        if ((rc = make_act_tmap(&mxl, x_lo, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, csw, csh))) return rc;
         if ((rc = make_wgt_tmap(&mwl, w_lo, w_cols, w_rows, w_taps, BLOCK_K, block_n))) return rc;
     } else {
         mxl = mxh;
         mwl = mwh;
     }
     p.N = N;
-    p.cs = cs;
+    p.csh = csh;
+    p.csw = csw;
     p.tiles_h = ceil_div(p.TOH, TILE_H);
     p.tiles_w = ceil_div(p.TOW, TILE_W);
     p.n_blocks = p.Cout_p / block_n;
@@ -411,7 +412,30 @@ int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi
     p.n_r = KH; p.n_s = KW;
     p.dh0 = -pad; p.dh_step = 1; p.dw0 = -pad; p.dw_step = 1;
     p.w_r0 = 0; p.w_rstep = 1; p.w_s0 = 0; p.w_sstep = 1; p.KW = KW;
-    return run_conv_tc(x_hi, x_lo, x_ld, H, W, w_hi, w_lo, Cout_p, Cin_p, KH * KW, p, N, stride, stream);
+    return run_conv_tc(x_hi, x_lo, x_ld, H, W, w_hi, w_lo, Cout_p, Cin_p, KH * KW, p, N, stride, stride, stream);
+}
+
+// Generic "tap list" convolution: z[n,oh,ow,:] = bias + addend + sum_{i<n_r, j<n_s} x[n, oh*csh + dh0 + i*dh_step,
+// ow*csw + dw0 + j*dw_step, :] . w[i*n_s + j]      (x out of bounds = 0).
+// Serves the 4-pixel channel-packed forms of the 13-band convolutions (engine.py: conv_small_in / conv_small_out).
+int conv2d_taps_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
+                   const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int OH, int OW,
+                   int Cin_p, int Cout_p, int n_r, int n_s, int dh0, int dh_step, int dw0, int dw_step, int csh, int csw,
+                   cudaStream_t stream) {
+    FCD_CHECK_ARG(OH > 0 && OW > 0 && n_r > 0 && n_s > 0 && csh >= 1 && csw >= 1, "conv2d_taps_tc: bad geometry");
+    FCD_CHECK_ARG(Cin_p % 64 == 0 && Cout_p % 64 == 0, "conv2d_taps_tc: channel counts must be multiples of 64");
+    FCD_CHECK_ARG(z_ld % 4 == 0 && x_ld % 8 == 0 && addend_ld % 4 == 0, "conv2d_taps_tc: pitches must keep 16-byte alignment");
+    FCD_CHECK_ARG(TILE_W * csw <= 256 && TILE_H * csh <= 256, "conv2d_taps_tc: coordinate scale too large for a TMA box");
+    ConvTcParams p{};
+    p.bias = bias; p.addend = addend; p.addend_ld = addend_ld; p.z = z;
+    p.stat_sum = nullptr; p.stat_sqsum = nullptr; p.z_ld = z_ld;
+    p.OH = OH; p.OW = OW; p.TOH = OH; p.TOW = OW;
+    p.out_sh = 1; p.out_oh = 0; p.out_sw = 1; p.out_ow = 0;
+    p.Cin_p = Cin_p; p.Cout_p = Cout_p;
+    p.n_r = n_r; p.n_s = n_s;
+    p.dh0 = dh0; p.dh_step = dh_step; p.dw0 = dw0; p.dw_step = dw_step;
+    p.w_r0 = 0; p.w_rstep = 1; p.w_s0 = 0; p.w_sstep = 1; p.KW = n_s;
+    return run_conv_tc(x_hi, x_lo, x_ld, XH, XW, w_hi, w_lo, Cout_p, Cin_p, n_r * n_s, p, N, csh, csw, stream);
 }
 
 // Stride-2 dgrad on the tcgen05 engine: the input-gradient pixels split into stride*stride parity classes; each class
@@ -446,7 +470,7 @@ int conv2d_dgrad_strided_tc(const void* dz_hi, const void* dz_lo, int dz_ld, con
             p.dh0 = (ph + pad - r0) / stride; p.dh_step = -1;
             p.dw0 = (pw + pad - s0) / stride; p.dw_step = -1;
             p.w_r0 = KH - 1 - r0; p.w_rstep = -stride; p.w_s0 = KW - 1 - s0; p.w_sstep = -stride; p.KW = KW;
-            int rc = run_conv_tc(dz_hi, dz_lo, dz_ld, OH, OW, wT_hi, wT_lo, Cin_p, Cout_p, KH * KW, p, N, 1, stream);
+            int rc = run_conv_tc(dz_hi, dz_lo, dz_ld, OH, OW, wT_hi, wT_lo, Cin_p, Cout_p, KH * KW, p, N, 1, 1, stream);
             if (rc) return rc;
         }
     }

@@ -83,6 +83,34 @@ __global__ void stage_kernel(const float* __restrict__ src, const float* __restr
     }
 }
 
+// NCHW fp32 (N,C<=16,H,W) -> split NHWC (N,H,W+M,64) with FOUR horizontally adjacent pixels packed into the channel
+// axis: dst[n,h,w'',j*16+c] = src[n,c,h,w''-M+j] (0 outside).  A 9x9 convolution over 13 bands then needs
+// ceil(9/4) = 3 taps of 64 channels per filter row instead of 9 (engine.py: conv_small_in / conv_small_out).
+__global__ void stage_pack4_kernel(const float* __restrict__ src, int C, int H, int W, int M, long long npix_out,
+                                   __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (pix >= npix_out) return;
+    const int Wp = W + M;
+    const int wq = static_cast<int>(pix % Wp);
+    const long long nh = pix / Wp;
+    const int h = static_cast<int>(nh % H);
+    const long long n = nh / H;
+    const float* s = src + n * C * static_cast<long long>(H) * W + static_cast<long long>(h) * W;
+    const long long HW = static_cast<long long>(H) * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int w = wq - M + j;
+        const bool in = w >= 0 && w < W;
+#pragma unroll
+        for (int c0 = 0; c0 < 16; c0 += 8) {
+            F8 r;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r.v[k] = (in && c0 + k < C) ? s[(c0 + k) * HW + w] : 0.f;
+            st_split8(hi, lo, static_cast<size_t>(pix) * 64 + j * 16 + c0, r);
+        }
+    }
+}
+
 // fp32 NHWC (pitch ld) -> NCHW fp32 (N,C,H,W); `accumulate` adds into dst.
 __global__ void unstage_kernel(const float* __restrict__ src, int ld, int C, long long HW, long long npix,
                                float* __restrict__ dst, int accumulate) {
@@ -601,6 +629,14 @@ int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, i
     const long long npix = 1LL * N * H * W;
     stage_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, mask, C, Cp, 1LL * H * W, npix, BF(dst_hi),
                                                                   BF(dst_lo), dst_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, int M, void* dst_hi, void* dst_lo, void* stream) {
+    FCD_CHECK_ARG(src && dst_hi && C >= 1 && C <= 16 && M >= 0, "fcd_stage_nchw_to_split_pack4: needs 1 <= C <= 16");
+    const long long npix = 1LL * N * H * (W + M);
+    stage_pack4_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, C, H, W, M, npix, BF(dst_hi), BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

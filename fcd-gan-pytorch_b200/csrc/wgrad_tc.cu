@@ -18,7 +18,7 @@ namespace fcd {
 using namespace tc;
 
 int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
-                  int box_h, int estride);
+                  int box_h, int estride_w, int estride_h);
 
 namespace {
 
@@ -41,7 +41,8 @@ struct WCfg {
 struct WgradParams {
     float* ws;            // [R*64][Cout_p] fp32, zero-initialised by the host wrapper
     int N, OH, OW;
-    int Cin_p, Cout_p, KH, KW, pad, stride;
+    int Cin_p, Cout_p, KH, KW, stride;   // KH x KW = the tap grid iterated (n_r x n_s for the generic tap-list form)
+    int h_off, w_off, s_step;           // x pixel of tap (r, s) for output pixel (h, w): (h*stride + r + h_off, w*stride + s*s_step + w_off)
     int cchunks, R;       // row groups = taps * cchunks
     int m_blocks, n_blocks, ksplit;
     int tiles_h, tiles_w;
@@ -111,7 +112,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 for (int sub = 0; sub < 2; ++sub) {
                     const int r = tapv[sub] / p.KW, s = tapv[sub] % p.KW;
                     // stride 2: the x tensor map has elementStrides 2, so the box picks every other pixel
-                    const int xw = w0 * p.stride + s - p.pad, xh = h0 * p.stride + r - p.pad;
+                    const int xw = w0 * p.stride + s * p.s_step + p.w_off, xh = h0 * p.stride + r + p.h_off;
                     tma_load_4d(st + sub * SUB_BYTES, &map_x_hi, &full_bar[stage], cbv[sub] * 64, xw, xh, n);
                     if (SPLIT)
                         tma_load_4d(st + C::A_BYTES + sub * SUB_BYTES, &map_x_lo, &full_bar[stage], cbv[sub] * 64, xw, xh, n);
@@ -267,11 +268,13 @@ static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CU
     return FCD_OK;
 }
 
-int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz_hi, const void* dz_lo, int dz_ld,
-                    float* dw, int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH, int KW, int stride,
-                    int pad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
-    const size_t need = wgrad_tc_workspace(N, H, W, Cin_p, Cout_p, KH, KW, pad);
+// Core: dW[(r, s)][ci][co] (+)= sum_{n, h < GH, w < GW} x[n, h*stride + r + h_off, w*stride + s*s_step + w_off, ci] * dz[n, h, w, co]
+// for r < n_r, s < n_s (x out of bounds = 0), written as fp32 OIHW [Cout][Cin][n_r][n_s].
+static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* dz_hi, const void* dz_lo,
+                         int dz_ld, int GH, int GW, float* dw, int N, int Cin, int Cin_p, int Cout, int Cout_p, int n_r,
+                         int n_s, int stride, int h_off, int w_off, int s_step, int accumulate, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+    const size_t need = sizeof(float) * static_cast<size_t>(n_r) * n_s * Cin_p * Cout_p;
     FCD_CHECK_ARG(workspace && workspace_bytes >= need, "conv2d_wgrad_tc: workspace too small (%zu < %zu)",
                   workspace_bytes, need);
     FCD_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0, "conv2d_wgrad_tc: pitches must be multiples of 8");
@@ -279,14 +282,15 @@ int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz
     const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
     WgradParams p;
     p.ws = static_cast<float*>(workspace);
-    p.N = N; p.OH = OH; p.OW = OW;
-    p.Cin_p = Cin_p; p.Cout_p = Cout_p; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
+    p.N = N; p.OH = GH; p.OW = GW;
+    p.Cin_p = Cin_p; p.Cout_p = Cout_p; p.KH = n_r; p.KW = n_s; p.stride = stride;
+    p.h_off = h_off; p.w_off = w_off; p.s_step = s_step;
     p.cchunks = Cin_p / 64;
-    p.R = KH * KW * p.cchunks;
+    p.R = n_r * n_s * p.cchunks;
     p.m_blocks = (p.R + 1) / 2;
     p.n_blocks = Cout_p / block_n;
-    p.tiles_h = ceil_div(OH, PT_H);
-    p.tiles_w = ceil_div(OW, PT_W);
+    p.tiles_h = ceil_div(GH, PT_H);
+    p.tiles_w = ceil_div(GW, PT_W);
     p.total_pt = 1LL * N * p.tiles_h * p.tiles_w;
     const long long mn = 1LL * p.m_blocks * p.n_blocks;
     long long ks = (2LL * sm_count() + mn - 1) / mn;
@@ -297,11 +301,11 @@ int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz
 
     CUtensorMap mxh, mxl, mgh, mgl;
     int rc;
-    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H, stride))) return rc;
-    if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H, 1))) return rc;
+    if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, XW, XH, N, x_ld, 64, PT_W, PT_H, stride, stride))) return rc;
+    if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, GW, GH, N, dz_ld, 64, PT_W, PT_H, 1, 1))) return rc;
     if (split) {
-        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, W, H, N, x_ld, 64, PT_W, PT_H, stride))) return rc;
-        if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, OW, OH, N, dz_ld, 64, PT_W, PT_H, 1))) return rc;
+        if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, XW, XH, N, x_ld, 64, PT_W, PT_H, stride, stride))) return rc;
+        if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, GW, GH, N, dz_ld, 64, PT_W, PT_H, 1, 1))) return rc;
     } else {
         mxl = mxh;
         mgl = mgh;
@@ -314,11 +318,29 @@ int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz
         rc = split ? launch_wgrad<64, true>(mxh, mxl, mgh, mgl, p, stream)
                    : launch_wgrad<64, false>(mxh, mxl, mgh, mgl, p, stream);
     if (rc) return rc;
-    const long long total = 1LL * Cout * Cin * KH * KW;
+    const long long total = 1LL * Cout * Cin * n_r * n_s;
     const int blocks = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
-    wgrad_scatter_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, Cin, Cout, Cin_p, Cout_p, KH, KW, accumulate);
+    wgrad_scatter_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, Cin, Cout, Cin_p, Cout_p, n_r, n_s, accumulate);
     FCD_LAUNCH_OK();
     return FCD_OK;
+}
+
+int conv2d_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, const void* dz_hi, const void* dz_lo, int dz_ld,
+                    float* dw, int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH, int KW, int stride,
+                    int pad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+    return wgrad_tc_core(x_hi, x_lo, x_ld, H, W, dz_hi, dz_lo, dz_ld, OH, OW, dw, N, Cin, Cin_p, Cout, Cout_p, KH, KW, stride,
+                         -pad, -pad, 1, accumulate, workspace, workspace_bytes, stream);
+}
+
+// Generic tap-list weight gradient (stride 1): see wgrad_tc_core; serves the 4-pixel channel-packed 13-band layers.
+int conv2d_taps_wgrad_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* dz_hi, const void* dz_lo,
+                         int dz_ld, int GH, int GW, float* dw, int N, int Cin, int Cin_p, int Cout, int Cout_p, int n_r,
+                         int n_s, int dh0, int dw0, int dw_step, int accumulate, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
+    FCD_CHECK_ARG(Cin_p % 64 == 0 && Cout_p % 64 == 0 && n_r > 0 && n_s > 0, "conv2d_taps_wgrad_tc: bad dims");
+    return wgrad_tc_core(x_hi, x_lo, x_ld, XH, XW, dz_hi, dz_lo, dz_ld, GH, GW, dw, N, Cin, Cin_p, Cout, Cout_p, n_r, n_s, 1, dh0,
+                         dw0, dw_step, accumulate, workspace, workspace_bytes, stream);
 }
 
 }  // namespace fcd

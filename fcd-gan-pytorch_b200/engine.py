@@ -145,16 +145,43 @@ class Act:
 class Z:
     """fp32 NHWC convolution output + BatchNorm statistics."""
 
-    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz")
+    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz", "pack_m")
 
     def __init__(self, t, N, H, W, C, Cp):
         self.t, self.N, self.H, self.W, self.C, self.Cp, self.ld = t, N, H, W, C, Cp, Cp
         self.sum = self.sqsum = None
         self.dz: Optional[Act] = None
+        self.pack_m = 0          # > 0: the producer wants its output gradient as a PackedAct with this left margin
 
     @property
     def npix(self):
         return self.N * self.H * self.W
+
+
+PACK_M = 4   # left margin (pixels) of a 4-pixel channel-packed tensor; must be >= the convolution padding
+
+
+class PackedAct:
+    """Split NHWC tensor (N, H, W + M, 64) holding a <= 16-channel image with FOUR horizontally adjacent pixels packed
+    into the channel axis: v[n, h, w'', j*16 + c] = image[n, c, h, w'' - M + j]  (fcd_stage_nchw_to_split_pack4).
+    A K x K convolution over it needs ceil(K/4) taps of 64 channels per filter row instead of K taps."""
+
+    __slots__ = ("hi", "lo", "N", "H", "W", "Wp", "C", "M")
+
+    def __init__(self, x_nchw: torch.Tensor, M: int = PACK_M):
+        N, C, H, W = x_nchw.shape
+        assert C <= 16
+        self.N, self.C, self.H, self.W, self.M, self.Wp = N, C, H, W, M, W + M
+        self.hi = torch.empty((N, H, self.Wp, 64), dtype=torch.bfloat16, device=x_nchw.device)
+        self.lo = torch.empty_like(self.hi) if _cfg["split"] else None
+        x_nchw = x_nchw.contiguous()
+        _call("fcd_stage_nchw_to_split_pack4", x_nchw.data_ptr(), N, C, H, W, M, self.hi.data_ptr(), _lib.ptr(self.lo))
+
+    def p_hi(self):
+        return self.hi.data_ptr()
+
+    def p_lo(self):
+        return None if self.lo is None else self.lo.data_ptr()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -202,6 +229,52 @@ def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
     if not capturing:
         cache[key] = (stamp, hi, lo)
     return hi, lo
+
+
+def _derived(w: torch.Tensor, key: str, fn) -> torch.Tensor:
+    """A tensor derived from parameter `w` by `fn` (small torch reshuffles of the weights), cached on the parameter
+    like the packed copies."""
+    cache = getattr(w, "_fcd_derived", None)
+    if cache is None:
+        cache = {}
+        try:
+            w._fcd_derived = cache
+        except AttributeError:
+            pass
+    stamp = (w.data_ptr(), w._version, _weight_epoch)
+    capturing = _capturing()
+    ent = None if capturing else cache.get(key)
+    if ent is not None and ent[0] == stamp:
+        return ent[1]
+    t = fn(w.detach())
+    if not capturing:
+        cache[key] = (stamp, t)
+    return t
+
+
+def _w_pack4_in(w: torch.Tensor) -> torch.Tensor:
+    """[Cout][C<=16][KH][KW] -> fake OIHW [Cout][64][KH][ceil(KW/4)] with W'[co][j*16+c][r][g] = w[co][c][r][4g+j]."""
+    Cout, C, KH, KW = w.shape
+    ng = (KW + 3) // 4
+    wp = w.new_zeros((Cout, 16, KH, ng * 4))
+    wp[:, :C, :, :KW] = w
+    return wp.view(Cout, 16, KH, ng, 4).permute(0, 4, 1, 2, 3).reshape(Cout, 64, KH, ng).contiguous()
+
+
+def _w_unpack4_in(dwp: torch.Tensor, C: int, KW: int) -> torch.Tensor:
+    """inverse of _w_pack4_in for a gradient: [Cout][64][KH][ng] -> [Cout][C][KH][KW]."""
+    Cout, _, KH, ng = dwp.shape
+    return dwp.view(Cout, 4, 16, KH, ng).permute(0, 2, 3, 4, 1).reshape(Cout, 16, KH, ng * 4)[:, :C, :, :KW]
+
+
+def _w_pack4_out(w: torch.Tensor) -> torch.Tensor:
+    """[Cout<=16][Cin][KH][KW] -> fake OIHW [64][Cin][KH][KW+3] with Wq[j*16+co][ci][r][s''] = w[co][ci][r][s''-j]:
+    column j*16+co produces output pixel 4q+j, channel co."""
+    Cout, Cin, KH, KW = w.shape
+    wq = w.new_zeros((4, 16, Cin, KH, KW + 3))
+    for j in range(4):
+        wq[j, :Cout, :, :, j:j + KW] = w
+    return wq.view(64, Cin, KH, KW + 3)
 
 
 def _ws(device, nbytes: int) -> torch.Tensor:
@@ -367,6 +440,108 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
                       wd_hi.data_ptr(), _lib.ptr(wd_lo), addend, x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW,
                       stride, pad, _cfg["engine"], tag=f"conv_dgrad_{deng} {shape}", flops=flops)
             x.mark_ready()
+        z.dz = None
+
+    tape.push(backward)
+    return z
+
+
+def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.Tensor], pad: int, stats: bool) -> Z:
+    """Stride-1 convolution whose INPUT has <= 16 channels (Generator head Module.py:146, Segmentor first layer
+    Module.py:26), on a 4-pixel channel-packed input: ceil(KW/4) taps of K = 64 per filter row.  No input gradient
+    (the input is data)."""
+    Cout, C, KH, KW = w.shape
+    assert C == xp.C
+    ng, M, N = (KW + 3) // 4, xp.M, xp.N
+    assert pad <= M
+    Cout_p = pad_ch(Cout)
+    OH, OW = xp.H + 2 * pad - KH + 1, xp.W + 2 * pad - KW + 1
+    wf = _derived(w, "pack4_in", _w_pack4_in)
+    w_hi, w_lo = _packed(wf, Cout_p, 64, 0, "pack4_in")
+    bias = None if b is None else _padded_vec(b, Cout_p)
+    zt = torch.empty((N, OH, OW, Cout_p), dtype=torch.float32, device=tape.device)
+    z = Z(zt, N, OH, OW, Cout, Cout_p)
+    flops = 2.0 * N * OH * OW * Cout * C * KH * KW
+    shape = f"{KH}x{KW}s1 {C}->{Cout}"
+    _call("fcd_conv2d_taps_fwd", xp.p_hi(), xp.p_lo(), 64, xp.H, xp.Wp, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
+          zt.data_ptr(), z.ld, N, OH, OW, 64, Cout_p, KH, ng, -pad, 1, -pad + M, 4, 1, 1,
+          tag=f"conv_fwd_tc_pack4 {shape}", flops=flops)
+    if stats:
+        st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
+        z.sum, z.sqsum = st[0], st[1]
+        _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
+
+    def backward(tape):
+        dz = z.dz
+        assert dz is not None
+        gw, acc = tape.pgrad(w)
+        dwp = torch.empty((Cout, 64, KH, ng), dtype=torch.float32, device=tape.device)
+        dbt = torch.empty((Cout,), dtype=torch.float32, device=tape.device) if b is not None else None
+        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(64, Cout_p, KH, ng)
+        ws = _ws(tape.device, nbytes)
+        _call("fcd_conv2d_taps_wgrad", xp.p_hi(), xp.p_lo(), 64, xp.H, xp.Wp, dz.p_hi(), dz.p_lo(), dz.ld, OH, OW,
+              dwp.data_ptr(), _lib.ptr(dbt), N, 64, 64, Cout, Cout_p, KH, ng, -pad, -pad + M, 4, 0, ws.data_ptr(), nbytes,
+              tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
+        g = _w_unpack4_in(dwp, C, KW)
+        gw.add_(g) if acc else gw.copy_(g)
+        if b is not None:
+            gb, accb = tape.pgrad(b)
+            gb.add_(dbt) if accb else gb.copy_(dbt)
+        z.dz = None
+
+    tape.push(backward)
+    return z
+
+
+def conv_small_out(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, pad: int) -> Z:
+    """Stride-1 convolution whose OUTPUT has <= 16 channels (Generator tail Module.py:158): the 64-wide N dimension
+    of the MMA produces FOUR adjacent output pixels x 16 channel slots per row (TMA reads every 4th input pixel), the
+    output is a plain NHWC tensor with 16 channel slots; dgrad / wgrad run on the 4-pixel channel-packed output
+    gradient.  Requires OW % 4 == 0."""
+    Cout, Cin, KH, KW = w.shape
+    assert Cin == x.C and Cout <= 16
+    N, H, W = x.N, x.H, x.W
+    OH, OW = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    assert OW % 4 == 0 and pad <= PACK_M
+    ng, M = (KW + 3) // 4, PACK_M
+    wq = _derived(w, "pack4_out", _w_pack4_out)
+    w_hi, w_lo = _packed(wq, 64, x.Cp, 0, "pack4_out")
+    bias = _derived(b, "pack4_bias", lambda t: torch.cat([_padded_vec(t, 16)] * 4))
+    zt = torch.empty((N, OH, OW, 16), dtype=torch.float32, device=tape.device)
+    z = Z(zt, N, OH, OW, Cout, 16)
+    z.pack_m = M
+    flops = 2.0 * N * OH * OW * Cout * Cin * KH * KW
+    shape = f"{KH}x{KW}s1 {Cin}->{Cout}"
+    _call("fcd_conv2d_taps_fwd", x.p_hi(), x.p_lo(), x.ld, H, W, w_hi.data_ptr(), _lib.ptr(w_lo), bias.data_ptr(), None, 0,
+          zt.data_ptr(), 64, N, OH, OW // 4, x.Cp, 64, KH, KW + 3, -pad, 1, -pad, 1, 1, 4,
+          tag=f"conv_fwd_tc_pack4 {shape}", flops=flops)
+
+    def backward(tape):
+        dzp = z.dz
+        assert isinstance(dzp, PackedAct), "conv_small_out backward: packed output gradient missing"
+        dev = tape.device
+        gw, acc = tape.pgrad(w)
+        gb, accb = tape.pgrad(b)
+        # wgrad: T[(r,g)][ci][j*16+co] = sum x[oh+r-pad, ow''+4g+3-M-pad, ci] * dzp[oh, ow'', j*16+co] = dw[co][ci][r][4g+3-j]
+        dwp = torch.empty((64, Cin, KH, ng), dtype=torch.float32, device=dev)
+        db64 = torch.empty((64,), dtype=torch.float32, device=dev)
+        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(x.Cp, 64, KH, ng)
+        ws = _ws(dev, nbytes)
+        _call("fcd_conv2d_taps_wgrad", x.p_hi(), x.p_lo(), x.ld, H, W, dzp.p_hi(), dzp.p_lo(), 64, OH, dzp.Wp, dwp.data_ptr(),
+              db64.data_ptr(), N, Cin, x.Cp, 64, 64, KH, ng, -pad, 3 - M - pad, 4, 0, ws.data_ptr(), nbytes,
+              tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
+        g = dwp.view(4, 16, Cin, KH, ng).flip(0).permute(1, 2, 3, 4, 0).reshape(16, Cin, KH, ng * 4)[:Cout, :, :, :KW]
+        gw.add_(g) if acc else gw.copy_(g)
+        gb.add_(db64[:Cout]) if accb else gb.copy_(db64[:Cout])
+        # dgrad: dx[h,w,ci] = sum_{r',g} dzp[h+r'-ph, w+4g-pw+M, :] . W''[ci][:][r'][g],  W'' = pack4_in(flip(w)^T)
+        wd = _derived(w, "pack4_dgrad", lambda t: _w_pack4_in(t.flip(2, 3).permute(1, 0, 2, 3)))
+        wd_hi, wd_lo = _packed(wd, x.Cp, 64, 0, "pack4_dgrad")
+        gx = x.grad
+        addend = gx.data_ptr() if x.ready else None
+        _call("fcd_conv2d_taps_fwd", dzp.p_hi(), dzp.p_lo(), 64, OH, dzp.Wp, wd_hi.data_ptr(), _lib.ptr(wd_lo), None, addend, x.ld,
+              gx.data_ptr(), x.ld, N, H, W, 64, x.Cp, KH, ng, -(KH - 1 - pad), 1, -(KW - 1 - pad) + M, 4, 1, 1,
+              tag=f"conv_dgrad_tc_pack4 {shape}", flops=flops)
+        x.mark_ready()
         z.dz = None
 
     tape.push(backward)
@@ -621,6 +796,9 @@ def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:
 
     def backward(tape):
         dout = grad_slot["dout"].contiguous()
+        if z.pack_m:
+            z.dz = PackedAct(dout, z.pack_m)
+            return
         dz = Act.empty(z.N, z.H, z.W, z.C, tape.device, z.Cp)
         _call("fcd_stage_nchw_to_split", dout.data_ptr(), None, z.N, z.C, z.H, z.W, dz.p_hi(), dz.p_lo(), dz.ld, dz.Cp)
         z.dz = dz

@@ -31,7 +31,10 @@ def _check_input(x: torch.Tensor, channels: int, what: str):
 def _double_conv(tape, dc: "DoubleConv", x: E.Act, training: bool, out=None, x_needs_grad=True) -> E.Act:
     """(conv3x3 p1 -> BN -> ReLU) x 2, Module.py:18-35."""
     seq = dc.double_conv
-    z = E.conv(tape, x, seq[0].weight, seq[0].bias, 1, 1, stats=training, x_needs_grad=x_needs_grad)
+    if isinstance(x, E.PackedAct):      # <= 16-band input without a gradient: 4-pixel channel-packed first conv
+        z = E.conv_small_in(tape, x, seq[0].weight, seq[0].bias, 1, stats=training)
+    else:
+        z = E.conv(tape, x, seq[0].weight, seq[0].bias, 1, 1, stats=training, x_needs_grad=x_needs_grad)
     m = E.bn_act(tape, z, _bn(seq[1]), training, E.ACT_RELU)
     z = E.conv(tape, m, seq[3].weight, seq[3].bias, 1, 1, stats=training)
     return E.bn_act(tape, z, _bn(seq[4]), training, E.ACT_RELU, out=out)
@@ -190,8 +193,12 @@ class Segmentor(nn.Module):
         def fn(tape, inputs, need):
             training = self.training
             N, _, H, W = inputs[0].shape
-            a = E.stage_input(tape, inputs[0], need[0])
-            b = E.stage_input(tape, inputs[1], need[1])
+            packed = self.n_channels <= 16 and not (need[0] or need[1])
+            if packed:
+                a, b = E.PackedAct(inputs[0]), E.PackedAct(inputs[1])
+            else:
+                a = E.stage_input(tape, inputs[0], need[0])
+                b = E.stage_input(tape, inputs[1], need[1])
             enc = [self.inc, self.down1.maxpool_conv[1], self.down2.maxpool_conv[1], self.down3.maxpool_conv[1],
                    self.down4.maxpool_conv[1]]
             ups = [self.up4, self.up3, self.up2, self.up1]       # ups[l] consumes the level-l skip
@@ -224,7 +231,7 @@ class Segmentor(nn.Module):
                 x = ups[l]._run(tape, x, cats[l], up_slot, training)
             slot = {}
             out = E.outconv_sigmoid(tape, x, self.outc.conv.weight, self.outc.conv.bias, slot)
-            return out, slot, [a, b]
+            return out, slot, ([None, None] if packed else [a, b])
 
         return E.run_net(self, fn, x1, x2)
 
@@ -272,15 +279,24 @@ class Generator(nn.Module):
 
         def fn(tape, inputs, need):
             training = self.training
-            a = E.stage_input(tape, inputs[0], need[0])
-            z = E.conv(tape, a, self.block1[0].weight, self.block1[0].bias, 1, 4, stats=False, x_needs_grad=need[0])
+            W = inputs[0].shape[3]
+            if self.n_channels <= 16 and not need[0]:
+                # 13-band head on the 4-pixel channel-packed input (3 taps of K = 64 per filter row instead of 9)
+                a = None
+                z = E.conv_small_in(tape, E.PackedAct(inputs[0]), self.block1[0].weight, self.block1[0].bias, 4, stats=False)
+            else:
+                a = E.stage_input(tape, inputs[0], need[0])
+                z = E.conv(tape, a, self.block1[0].weight, self.block1[0].bias, 1, 4, stats=False, x_needs_grad=need[0])
             b1 = E.bn_act(tape, z, None, training, E.ACT_PRELU, slope=self.block1[1].weight)
             h = b1
             for blk in (self.block2, self.block3, self.block4, self.block5, self.block6):
                 h = _residual_block(tape, blk, h, training)
             z = E.conv(tape, h, self.block7[0].weight, self.block7[0].bias, 1, 1, stats=training)
             s = E.bn_act(tape, z, _bn(self.block7[1]), training, E.ACT_NONE, residual=b1)   # block1 + block7
-            z = E.conv(tape, s, self.block8.weight, self.block8.bias, 1, 4, stats=False)
+            if self.n_channels <= 16 and W % 4 == 0:
+                z = E.conv_small_out(tape, s, self.block8.weight, self.block8.bias, 4)     # 4 output pixels per MMA row
+            else:
+                z = E.conv(tape, s, self.block8.weight, self.block8.bias, 1, 4, stats=False)
             slot = {}
             return E.z_to_nchw(tape, z, slot), slot, [a]
 

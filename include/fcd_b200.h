@@ -94,6 +94,27 @@ int fcd_conv2d_wgrad(const void* x_hi, const void* x_lo, int x_ld, const void* d
                      size_t workspace_bytes, int engine, void* stream);
 
 
+/* ---- generic tap-list convolution (tcgen05 engine only; channel counts multiples of 64) ----------------------
+ * z[n,oh,ow,:] = bias + addend + sum_{i<n_r, j<n_s} x[n, oh*csh + dh0 + i*dh_step, ow*csw + dw0 + j*dw_step, :] . w[i*n_s+j]
+ * with x (N, XH, XW, Cin_p) split, out-of-bounds pixels = 0, w packed [n_r*n_s][Cout_p][Cin_p] (fcd_pack_conv_weight
+ * mode 0 of an OIHW tensor with KH = n_r, KW = n_s).  csh / csw > 1 read every csh-th / csw-th pixel (TMA element
+ * strides).  This is how the 13-band layers of the Generator (Module.py:146,158) and the Segmentor's first conv
+ * (Module.py:26) run: four adjacent pixels are packed into the 64-wide channel axis (fcd_stage_nchw_to_split_pack4),
+ * which cuts a 9x9 filter row from 9 taps to 3. */
+int fcd_conv2d_taps_fwd(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
+                        const float* bias, const float* addend, int addend_ld, float* z, int z_ld, int N, int OH, int OW,
+                        int Cin_p, int Cout_p, int n_r, int n_s, int dh0, int dh_step, int dw0, int dw_step, int csh, int csw,
+                        void* stream);
+/* dw[co][ci][r][s] (+)= sum_{n, h<GH, w<GW} x[n, h + r + dh0, w + s*dw_step + dw0, ci] * dz[n,h,w,co]  (fp32 OIHW with
+ * KH = n_r, KW = n_s, logical Cout x Cin);  db[co] (+)= sum dz. */
+size_t fcd_conv2d_taps_wgrad_workspace(int Cin_p, int Cout_p, int n_r, int n_s);
+int fcd_conv2d_taps_wgrad(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* dz_hi, const void* dz_lo,
+                          int dz_ld, int GH, int GW, float* dw, float* db, int N, int Cin, int Cin_p, int Cout, int Cout_p,
+                          int n_r, int n_s, int dh0, int dw0, int dw_step, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* NCHW fp32 (N, C <= 16, H, W) -> split NHWC (N, H, W+M, 64): dst[n,h,w'',j*16+c] = src[n,c,h,w''-M+j], j = 0..3. */
+int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, int M, void* dst_hi, void* dst_lo, void* stream);
+
 /* ==== HBM-bound glue between the convolutions (elementwise.cu) =====================================
  * "split" outputs are conv operands (bf16 hi/lo planes); fp32 NHWC tensors are conv results / gradients. */
 

@@ -136,6 +136,28 @@ def test_discriminator(name):
     _check_running(net, sd_ref)
 
 
+@pytest.mark.parametrize("kind,name", [("generator", "g13_train.pt"), ("segmentor", "s13_bilinear_even.pt"),
+                                       ("segmentor", "s4_bilinear_odd.pt")])
+def test_data_inputs_take_the_packed_13_band_path(kind, name):
+    """Inputs that do not require a gradient (the case in every training loop: x, y are data) run the <= 16-band layers on
+    the 4-pixel channel-packed tcgen05 path; outputs and parameter gradients must match the reference all the same."""
+    fb.set_precision("parity")
+    f = load_golden(name)
+    if kind == "generator":
+        net = _load(fb.Generator(f["C"]), O.generator_spec(f["C"]), f["seed"]).train(f["train"])
+        out = net(f["x"].to(DEV))
+        ref_out, tol = f["y"], GRAD_L2
+    else:
+        net = _load(fb.Segmentor(f["C"], 1, f["bilinear"]), O.segmentor_spec(f["C"], 1, f["bilinear"]), f["seed"]).train(f["train"])
+        out = net(f["x"].to(DEV), f["y"].to(DEV))
+        ref_out, tol = f["cmap"], GRAD_L2_SEG
+    assert rel_err(out, ref_out) < OUT_TOL
+    (out * f["r"].to(DEV)).sum().backward()
+    _, _, grads, sd_ref = _oracle(kind, f)
+    _check_grads(net, grads, name, tol)
+    _check_running(net, sd_ref)
+
+
 def test_generator_double_backward_and_fast_mode():
     """retain_graph=True + second backward (Demo_USSS.py:327,338) accumulates 2x the gradient; 'fast' precision
     stays within bf16-class error of the reference."""

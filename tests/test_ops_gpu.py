@@ -373,3 +373,66 @@ def test_stage_roundtrip_and_mask():
     out = torch.empty_like(x)
     _lib.call("fcd_unstage_split_to_nchw", a.p_hi(), a.p_lo(), a.ld, N, C, H, W, out.data_ptr(), S())
     assert rel(out, x * (1 - m)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,Cout,K,pad,H,W", [(13, 64, 9, 4, 20, 24), (4, 64, 3, 1, 19, 21), (3, 64, 9, 4, 33, 40), (16, 128, 3, 1, 8, 8)])
+def test_conv_small_in_pack4(C, Cout, K, pad, H, W):
+    """<= 16-band input convolution on the 4-pixel channel-packed input (Generator head Module.py:146, Segmentor first
+    layer Module.py:26): forward, BN statistics, wgrad, db vs F.conv2d autograd in fp64.  Tolerance 3e-5."""
+    torch.manual_seed(9)
+    N = 2
+    x = torch.randn(N, C, H, W, device=DEV)
+    w = (torch.randn(Cout, C, K, K, device=DEV) * 0.1).requires_grad_(True)
+    b = torch.randn(Cout, device=DEV).requires_grad_(True)
+    tape = E.Tape(DEV, True)
+    xp = E.PackedAct(x)
+    z = E.conv_small_in(tape, xp, w, b, pad, stats=True)
+    # reference on the bf16-pair-rounded operands
+    xr = joined(*split(x))
+    wr = joined(*split(w.detach())).requires_grad_(True)
+    br = b.detach().double().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=pad)
+    got = z.t[..., :Cout].permute(0, 3, 1, 2)
+    assert rel(got, ref) < 3e-5
+    assert rel(z.sum[:Cout], ref.sum(dim=(0, 2, 3))) < 1e-4 and rel(z.sqsum[:Cout], (ref * ref).sum(dim=(0, 2, 3))) < 1e-4
+    dz = torch.randn_like(ref).float()
+    z.dz = act_from(dz, Cp=z.Cp)
+    gr = act_value(z.dz)
+    tape.ops[-1](tape)
+    gw, gb = torch.autograd.grad(ref, (wr, br), gr)
+    assert rel(tape.pgrads[id(w)], gw) < 3e-5 and rel(tape.pgrads[id(b)], gb) < 3e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,K,pad,H,W", [(64, 13, 9, 4, 20, 24), (64, 4, 9, 4, 17, 32), (128, 3, 3, 1, 12, 8)])
+def test_conv_small_out_pack4(Cin, Cout, K, pad, H, W):
+    """<= 16-channel output convolution (Generator tail Module.py:158): four output pixels per MMA row; dgrad and wgrad on
+    the 4-pixel channel-packed output gradient.  Tolerance 3e-5."""
+    torch.manual_seed(10)
+    N = 2
+    x = torch.randn(N, Cin, H, W, device=DEV)
+    w = (torch.randn(Cout, Cin, K, K, device=DEV) * 0.05).requires_grad_(True)
+    b = torch.randn(Cout, device=DEV).requires_grad_(True)
+    tape = E.Tape(DEV, True)
+    a = tape.track(act_from(x))
+    z = E.conv_small_out(tape, a, w, b, pad)
+    xr = act_value(a).clone().requires_grad_(True)
+    wr = joined(*split(w.detach())).requires_grad_(True)
+    br = b.detach().double().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=pad)
+    got = z.t[..., :Cout].permute(0, 3, 1, 2)
+    assert rel(got, ref) < 3e-5
+    slot = {}
+    out = E.z_to_nchw(tape, z, slot)
+    assert rel(out, ref) < 3e-5
+    dy = torch.randn_like(out)
+    slot["dout"] = dy
+    pre = torch.randn(N, H, W, a.Cp, device=DEV)          # an already accumulated gradient (addend path)
+    a.grad.copy_(pre)
+    a.mark_ready()
+    tape.ops[-1](tape)      # z_to_nchw backward: packs dy
+    tape.ops[-2](tape)      # conv backward
+    gyr = joined(*split(dy))
+    gx, gw, gb = torch.autograd.grad(ref, (xr, wr, br), gyr)
+    assert rel(a.grad[..., :Cin].permute(0, 3, 1, 2), gx + pre[..., :Cin].permute(0, 3, 1, 2).double()) < 3e-5
+    assert rel(tape.pgrads[id(w)], gw) < 3e-5 and rel(tape.pgrads[id(b)], gb) < 3e-5
