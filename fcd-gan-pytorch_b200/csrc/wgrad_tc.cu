@@ -292,8 +292,13 @@ static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, i
     p.tiles_h = ceil_div(GH, PT_H);
     p.tiles_w = ceil_div(GW, PT_W);
     p.total_pt = 1LL * N * p.tiles_h * p.tiles_w;
+    // split-K so that the grid fills whole waves: one CTA per SM is resident (192 KB of shared memory), so the CTA count
+    // should be just BELOW a multiple of the SM count (a 300-CTA grid on 148 SMs runs three waves, the last one with 4 CTAs).
     const long long mn = 1LL * p.m_blocks * p.n_blocks;
-    long long ks = (2LL * sm_count() + mn - 1) / mn;
+    const long long sms = sm_count();
+    long long waves = (mn + sms - 1) / sms;          // waves needed without any split
+    if (waves < 2) waves = 2;
+    long long ks = (waves * sms) / mn;               // floor: ks * mn <= waves * sms
     if (ks < 1) ks = 1;
     if (ks > p.total_pt) ks = p.total_pt;
     p.pt_per_split = (p.total_pt + ks - 1) / ks;
