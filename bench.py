@@ -121,6 +121,12 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if args.max_seconds > 0:       # self-destruct: a hung collective must not hold N GPUs until an outer timeout
+        t_kill = threading.Timer(args.max_seconds, lambda: os._exit(3))
+        t_kill.daemon = True
+        t_kill.start()
+    if world > 1 and args.graph == "on":
+        os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
     if world > 1:
         local = P.init_from_env("nccl")
     else:
@@ -133,7 +139,8 @@ def run_ours(args):
     torch.manual_seed(0)
     netG, netD = fb.Generator(C).to(dev).train(), fb.Discriminator_SRGAN_simple(C).to(dev).train()
     P.broadcast_parameters([netG, netD])
-    # world > 1 stays eager: capturing the NCCL all-reduces hung on this stack (torch 2.11 / NCCL 2.28.9), see DESIGN.md §7
+    # world > 1 stays eager by default: capturing the NCCL all-reduces hung on this stack (torch 2.11 / NCCL 2.28.9),
+    # see DESIGN.md §7; `--graph on` forces the capture (thread-local capture mode, NCCL async error handling off).
     use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
     optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=use_graph)   # Demo_USSS.py:121
     optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=use_graph)                   # Demo_RSSS.py:157
@@ -173,7 +180,7 @@ def run_ours(args):
     if use_graph:
         try:
             from fcdgan_b200.graph import GraphedStep
-            gstep = GraphedStep(eager_step, data, warmup=3)
+            gstep = GraphedStep(eager_step, data, warmup=3, capture_error_mode="thread_local" if world > 1 else "global")
 
             def step(*inputs):                      # noqa: F811 — replay; inputs are copied into the static buffers
                 if inputs and inputs[0] is not data[0]:
@@ -187,7 +194,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()           # started BEFORE the warm-up: nvidia-smi's start-up stalls the driver for ~0.5 s
-    for _ in range(args.warmup):
+    # eager mode: torch's caching allocator needs ~8 iterations to reach a steady block layout (cudaMalloc bursts until
+    # then); the extra untimed iterations only apply when the step is not replayed from a graph.
+    n_warm = args.warmup if step is not eager_step else max(args.warmup, 8)
+    for _ in range(n_warm):
         step(*data)
     barrier()
     sampler.rows.clear()          # keep only samples taken during the timed region
@@ -363,6 +373,7 @@ def main():
     ap.add_argument("--precision", choices=["parity", "fast"], default="parity")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto", help="capture the iteration in a CUDA graph")
+    ap.add_argument("--max-seconds", type=float, default=0.0, help="hard-exit the process after this many seconds (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of the instrumented pass here")
     args = ap.parse_args()

@@ -22,7 +22,8 @@ from . import engine as E
 
 
 class GraphedStep:
-    def __init__(self, fn: Callable, static_inputs: Sequence[torch.Tensor], warmup: int = 3):
+    def __init__(self, fn: Callable, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
+                 capture_error_mode: str = "global"):
         self.fn = fn
         self.static_inputs = list(static_inputs)
         side = torch.cuda.Stream()
@@ -34,7 +35,8 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = E.launch_count
-        with torch.cuda.graph(self.graph):
+        # "thread_local" lets other threads (e.g. the NCCL watchdog) keep making CUDA calls during the capture
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.outputs = fn(*self.static_inputs)
         self.launches_per_replay = E.launch_count - n0      # libfcd_b200 C-ABI calls recorded in the graph
         E.bump_weight_epoch()
