@@ -1,5 +1,6 @@
 // api_conv.cu — C-ABI entry points for the convolution family + library-wide error plumbing.
 #include <stdarg.h>
+#include <string.h>
 
 #include "fcd_common.cuh"
 
@@ -46,6 +47,7 @@ int conv2d_taps_tc(const void*, const void*, int, int, int, const void*, const v
                    int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv2d_taps_wgrad_tc(const void*, const void*, int, int, int, const void*, const void*, int, int, int, float*, int, int, int,
                          int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+extern bool g_wgrad_halo_enabled;
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream);
 
@@ -57,6 +59,16 @@ extern "C" {
 
 const char* fcd_last_error(void) { return g_err; }
 int fcd_version(void) { return 100; }
+
+int fcd_set_option(const char* name, int value) {
+    FCD_CHECK_ARG(name, "fcd_set_option: null name");
+    if (strcmp(name, "wgrad_halo") == 0) {
+        g_wgrad_halo_enabled = value != 0;
+        return FCD_OK;
+    }
+    set_error(FCD_ERR_ARG, "fcd_set_option: unknown option '%s'", name);
+    return FCD_ERR_ARG;
+}
 
 int fcd_conv2d_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
     return conv_tc_supported(Cin_p, Cout_p, KH, KW, stride) ? 1 : 0;

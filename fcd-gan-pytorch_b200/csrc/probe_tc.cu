@@ -30,6 +30,7 @@ struct ProbeParams {
     int a_shift_rows, a_base_offset;
     int b_shift_rows, b_base_offset;
     int a_sbo, b_sbo;        // stride-byte-offset overrides (0 = 1024)
+    int a_lbo, a_kstep;      // leading-byte-offset / per-UMMA start advance overrides for A (0 = defaults)
 };
 
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeParams p) {
@@ -72,11 +73,12 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeParams p) {
             uint64_t da, db;
             if (!p.mn_major) {
                 // K-major: 16 bf16 = 32 bytes further along the 128-byte row
-                da = make_smem_desc(a0 + k * 32, 16, a_sbo, kSwizzle128, p.a_base_offset);
+                da = make_smem_desc(a0 + k * (p.a_kstep ? p.a_kstep : 32), 16, a_sbo, kSwizzle128, p.a_base_offset);
                 db = make_smem_desc(b0 + k * 32, 16, b_sbo, kSwizzle128, p.b_base_offset);
             } else {
                 // MN-major: K runs over rows; 16 rows = 2048 bytes; LBO = distance between 64-wide MN blocks
-                da = make_smem_desc(a0 + k * 2048, a_block_bytes, a_sbo, kSwizzle128, p.a_base_offset);
+                da = make_smem_desc(a0 + k * (p.a_kstep ? p.a_kstep : 2048), p.a_lbo ? p.a_lbo : a_block_bytes, a_sbo,
+                                    kSwizzle128, p.a_base_offset);
                 db = make_smem_desc(b0 + k * 2048, b_block_bytes, b_sbo, kSwizzle128, p.b_base_offset);
             }
             umma_f16(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
@@ -110,7 +112,7 @@ using namespace fcd;
 extern "C" int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks,
                                     int b_blocks, int mn_major, int n, int ksteps, int a_shift_rows,
                                     int a_base_offset, int b_shift_rows, int b_base_offset, int a_sbo, int b_sbo,
-                                    void* stream) {
+                                    int a_lbo, int a_kstep, void* stream) {
     FCD_CHECK_ARG(a && b && d, "umma_probe: null pointer");
     FCD_CHECK_ARG(n % 16 == 0 && n >= 16 && n <= 256, "umma_probe: bad N");
     ProbeParams p;
@@ -122,6 +124,7 @@ extern "C" int fcd_debug_umma_probe(const void* a, const void* b, float* d, int 
     p.a_shift_rows = a_shift_rows; p.a_base_offset = a_base_offset;
     p.b_shift_rows = b_shift_rows; p.b_base_offset = b_base_offset;
     p.a_sbo = a_sbo; p.b_sbo = b_sbo;
+    p.a_lbo = a_lbo; p.a_kstep = a_kstep;
     const int smem = ((a_blocks * a_rows * 128 + 1023) & ~1023) + b_blocks * b_rows * 128 + 2048;
     FCD_CHECK_ARG(smem <= 200 * 1024, "umma_probe: operands do not fit shared memory");
     FCD_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

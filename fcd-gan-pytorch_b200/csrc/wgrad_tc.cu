@@ -20,6 +20,8 @@ using namespace tc;
 int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w,
                   int box_h, int estride_w, int estride_h);
 
+bool g_wgrad_halo_enabled = true;    // FCD_WGRAD_HALO=0 (read by fcd_set_option) selects the per-tap-pair kernel
+
 namespace {
 
 constexpr int PT_H = 4, PT_W = 16;        // pixel tile = 64 pixels = K per stage
@@ -268,6 +270,227 @@ static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CU
     return FCD_OK;
 }
 
+// =====================================================================================================
+// Halo-reuse weight gradient (stride 1): one CTA owns (64 input channels) x (64 output channels) x (up to 16 taps).
+// Per K tile of 8 x 8 output pixels it stages the x tile ONCE with its halo ({64 ch, 8 + (n_s-1)*s_step, 8 + n_r-1} TMA
+// box) and the dz tile once; every tap is a ROW-SHIFTED VIEW of the staged x tile (MN-major UMMA descriptor whose start
+// address is moved by (r * halo_w + s * s_step) pixels, stride-byte-offset = halo_w * 128 so the 8-pixel groups follow
+// the halo pitch).  Two taps form one M = 128 operand: the descriptor's leading-byte-offset is the distance between the
+// two views.  All tap accumulators live in TMEM (64 columns per tap pair).  Versus wgrad_tc_kernel this moves 3.6x
+// fewer bytes L2 -> shared memory for a 3x3 layer (the x tile is no longer re-fetched per tap pair).
+// Descriptor semantics (SBO not a multiple of 1024, small LBO, shifted start) are pinned by scripts/probe_halo.py.
+// =====================================================================================================
+constexpr int HP = 8;                 // K tile = HP x HP output pixels
+constexpr int H_MAX_TAPS = 16;        // 8 accumulators x 64 TMEM columns
+constexpr int H_SMEM_BUDGET = 200 * 1024;
+
+struct WHaloParams {
+    float* ws;
+    int N, GH, GW;
+    int Cin_p, Cout_p;
+    int n_r, n_s, s_step, h_off, w_off;
+    int halo_w, halo_h;
+    int x_bytes;              // bytes of one staged x plane (halo_w * halo_h * 128), slot rounded up to 1024
+    int x_slot, stage_bytes, stages;
+    int taps_per_group, tap_groups;
+    int cchunks, n_blocks, ksplit;
+    int tiles_h, tiles_w;
+    long long total_pt, pt_per_split;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                  const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                  const WHaloParams p) {
+    constexpr int PLANES = SPLIT ? 2 : 1;
+    constexpr int G_BYTES = 64 * 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* done_bar = empty_bar + 8;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int nb = item % p.n_blocks; item /= p.n_blocks;
+    const int cb = item % p.cchunks;
+    const int tg = item / p.cchunks;
+    const int total_taps = p.n_r * p.n_s;
+    const int tap0 = tg * p.taps_per_group;
+    const int ntaps = (total_taps - tap0 < p.taps_per_group) ? total_taps - tap0 : p.taps_per_group;
+    const int npairs = (ntaps + 1) >> 1;
+    const long long pt_begin = ks * p.pt_per_split;
+    long long pt_end = pt_begin + p.pt_per_split;
+    if (pt_end > p.total_pt) pt_end = p.total_pt;
+    const uint32_t tmem_cols = npairs * 64 <= 64 ? 64 : npairs * 64 <= 128 ? 128 : npairs * 64 <= 256 ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x_hi);
+        tma_prefetch_desc(&map_g_hi);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t stage_tx = static_cast<uint32_t>((p.x_bytes + G_BYTES) * PLANES);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+                long long t = pt;
+                const int tw = static_cast<int>(t % p.tiles_w); t /= p.tiles_w;
+                const int th = static_cast<int>(t % p.tiles_h);
+                const int n = static_cast<int>(t / p.tiles_h);
+                const int h0 = th * HP, w0 = tw * HP;
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* st = smem + stage * p.stage_bytes;
+                mbar_expect_tx(&full_bar[stage], stage_tx);
+                tma_load_4d(st, &map_x_hi, &full_bar[stage], cb * 64, w0 + p.w_off, h0 + p.h_off, n);
+                if (SPLIT) tma_load_4d(st + p.x_slot, &map_x_lo, &full_bar[stage], cb * 64, w0 + p.w_off, h0 + p.h_off, n);
+                uint8_t* sg = st + p.x_slot * PLANES;
+                tma_load_4d(sg, &map_g_hi, &full_bar[stage], nb * 64, w0, h0, n);
+                if (SPLIT) tma_load_4d(sg + G_BYTES, &map_g_lo, &full_bar[stage], nb * 64, w0, h0, n);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+            const uint32_t sbo_a = static_cast<uint32_t>(p.halo_w) * 128u;   // 8-pixel groups follow the halo row pitch
+            const uint32_t kstep_a = 2u * sbo_a;                            // UMMA K = 16 pixels = two tile rows
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t first = 1;
+            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t x_hi = smem_u32(smem + stage * p.stage_bytes);
+                const uint32_t x_lo = x_hi + p.x_slot;
+                const uint32_t g_hi = x_hi + p.x_slot * PLANES;
+                const uint32_t g_lo = g_hi + G_BYTES;
+                for (int pr = 0; pr < npairs; ++pr) {
+                    int ta = tap0 + 2 * pr, tb = ta + 1;
+                    if (tb >= tap0 + ntaps) {      // odd tap count: the last pair re-uses the previous tap as its first half
+                        tb = ta;
+                        ta = ta - 1;
+                    }
+                    const uint32_t off_a = static_cast<uint32_t>((ta / p.n_s) * p.halo_w + (ta % p.n_s) * p.s_step) * 128u;
+                    const uint32_t off_b = static_cast<uint32_t>((tb / p.n_s) * p.halo_w + (tb % p.n_s) * p.s_step) * 128u;
+                    const uint32_t lbo = off_b - off_a;
+                    const uint32_t d_tmem = tmem_base + pr * 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da_hi = make_smem_desc(x_hi + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
+                        const uint64_t db_hi = make_smem_desc(g_hi + k * 2048, G_BYTES, 1024, kSwizzle128);
+                        umma_f16(d_tmem, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
+                        if (SPLIT) {
+                            const uint64_t da_lo = make_smem_desc(x_lo + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
+                            const uint64_t db_lo = make_smem_desc(g_lo + k * 2048, G_BYTES, 1024, kSwizzle128);
+                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                }
+                first = 0;
+                umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(done_bar);
+        }
+    } else if (pt_end > pt_begin) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;      // accumulator row: half = row / 64 (first / second tap of the pair), ci = row % 64
+        const int half = row >> 6;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        for (int pr = 0; pr < npairs; ++pr) {
+            int ta = tap0 + 2 * pr, tb = ta + 1;
+            bool live = true;
+            if (tb >= tap0 + ntaps) {
+                tb = ta;
+                ta = ta - 1;
+                live = half == 1;            // the duplicated first half is discarded
+            }
+            const int tap = half ? tb : ta;
+            float* dst = p.ws + (static_cast<size_t>(tap * p.cchunks + cb) * 64 + (row & 63)) * p.Cout_p + nb * 64;
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + pr * 64 + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        atomicAdd(reinterpret_cast<float4*>(dst + c + j),
+                                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                              __uint_as_float(v[j + 3])));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static bool wgrad_halo_fits(int n_r, int n_s, int s_step, bool split, WHaloParams* out) {
+    const int halo_w = HP + (n_s - 1) * s_step, halo_h = HP + n_r - 1;
+    if (n_r * n_s < 2 || halo_w > 256 || halo_h > 256) return false;
+    const int x_bytes = halo_w * halo_h * 128;
+    const int x_slot = (x_bytes + 1023) & ~1023;
+    const int stage_bytes = (x_slot + 64 * 128) * (split ? 2 : 1);
+    int stages = H_SMEM_BUDGET / stage_bytes;
+    if (stages < 2) return false;
+    if (stages > 6) stages = 6;
+    if (out) {
+        out->halo_w = halo_w; out->halo_h = halo_h; out->x_bytes = x_bytes; out->x_slot = x_slot;
+        out->stage_bytes = stage_bytes; out->stages = stages;
+    }
+    return true;
+}
+
+template <bool SPLIT>
+static int launch_wgrad_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mgh, const CUtensorMap& mgl,
+                             const WHaloParams& p, unsigned grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    const int smem_bytes = H_SMEM_BUDGET + 1024 + 256;
+    if (!attr_set) {
+        FCD_CUDA_OK(cudaFuncSetAttribute(wgrad_halo_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set = true;
+    }
+    wgrad_halo_kernel<SPLIT><<<grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mgh, mgl, p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+// 4D NHWC bf16 map with an arbitrary box (halo tiles); defined in conv_tc.cu
+int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int box_c, int box_w, int box_h,
+                  int estride_w, int estride_h);
+
 // Core: dW[(r, s)][ci][co] (+)= sum_{n, h < GH, w < GW} x[n, h*stride + r + h_off, w*stride + s*s_step + w_off, ci] * dz[n, h, w, co]
 // for r < n_r, s < n_s (x out of bounds = 0), written as fp32 OIHW [Cout][Cin][n_r][n_s].
 static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* dz_hi, const void* dz_lo,
@@ -279,6 +502,45 @@ static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, i
                   workspace_bytes, need);
     FCD_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0, "conv2d_wgrad_tc: pitches must be multiples of 8");
     const bool split = x_lo && dz_lo;
+    WHaloParams hp;
+    if (stride == 1 && g_wgrad_halo_enabled && wgrad_halo_fits(n_r, n_s, s_step, split, &hp)) {
+        hp.ws = static_cast<float*>(workspace);
+        hp.N = N; hp.GH = GH; hp.GW = GW; hp.Cin_p = Cin_p; hp.Cout_p = Cout_p;
+        hp.n_r = n_r; hp.n_s = n_s; hp.s_step = s_step; hp.h_off = h_off; hp.w_off = w_off;
+        hp.taps_per_group = H_MAX_TAPS;
+        hp.tap_groups = (n_r * n_s + H_MAX_TAPS - 1) / H_MAX_TAPS;
+        hp.cchunks = Cin_p / 64; hp.n_blocks = Cout_p / 64;
+        hp.tiles_h = ceil_div(GH, HP); hp.tiles_w = ceil_div(GW, HP);
+        hp.total_pt = 1LL * N * hp.tiles_h * hp.tiles_w;
+        const long long base = 1LL * hp.cchunks * hp.n_blocks * hp.tap_groups;
+        const long long sms = sm_count();
+        long long ks = base >= sms ? 1 : sms / base;          // fill one wave (1 CTA per SM is resident)
+        if (ks > hp.total_pt) ks = hp.total_pt;
+        if (ks < 1) ks = 1;
+        hp.pt_per_split = (hp.total_pt + ks - 1) / ks;
+        hp.ksplit = static_cast<int>((hp.total_pt + hp.pt_per_split - 1) / hp.pt_per_split);
+        CUtensorMap mxh, mxl, mgh, mgl;
+        int rc;
+        if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, XW, XH, N, x_ld, 64, hp.halo_w, hp.halo_h, 1, 1))) return rc;
+        if ((rc = make_act_tmap(&mgh, dz_hi, Cout_p, GW, GH, N, dz_ld, 64, HP, HP, 1, 1))) return rc;
+        if (split) {
+            if ((rc = make_act_tmap(&mxl, x_lo, Cin_p, XW, XH, N, x_ld, 64, hp.halo_w, hp.halo_h, 1, 1))) return rc;
+            if ((rc = make_act_tmap(&mgl, dz_lo, Cout_p, GW, GH, N, dz_ld, 64, HP, HP, 1, 1))) return rc;
+        } else {
+            mxl = mxh;
+            mgl = mgh;
+        }
+        FCD_CUDA_OK(cudaMemsetAsync(workspace, 0, need, stream));
+        const unsigned grid = static_cast<unsigned>(base * hp.ksplit);
+        rc = split ? launch_wgrad_halo<true>(mxh, mxl, mgh, mgl, hp, grid, stream)
+                   : launch_wgrad_halo<false>(mxh, mxl, mgh, mgl, hp, grid, stream);
+        if (rc) return rc;
+        const long long total = 1LL * Cout * Cin * n_r * n_s;
+        const int blocks = static_cast<int>((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+        wgrad_scatter_kernel<<<blocks, 256, 0, stream>>>(hp.ws, dw, Cin, Cout, Cin_p, Cout_p, n_r, n_s, accumulate);
+        FCD_LAUNCH_OK();
+        return FCD_OK;
+    }
     const int block_n = (Cout_p % 128 == 0) ? 128 : 64;
     WgradParams p;
     p.ws = static_cast<float*>(workspace);

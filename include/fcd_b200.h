@@ -46,6 +46,8 @@ extern "C" {
 
 const char* fcd_last_error(void);
 int fcd_version(void);
+/* Library-wide switches for A/B measurements: "wgrad_halo" (default 1) = halo-reuse weight-gradient kernel. */
+int fcd_set_option(const char* name, int value);
 /* 1 if the tcgen05 engine can serve this convolution, else 0 (then AUTO uses SIMT). */
 int fcd_conv2d_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);
 
@@ -247,7 +249,7 @@ int fcd_msssim_combine_bwd(const double* sums, const double* counts, const float
 /* bring-up probe for the tcgen05 shared-memory descriptor semantics (scripts/gpu_probe.py); not on the product path */
 int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks, int b_blocks,
                          int mn_major, int n, int ksteps, int a_shift_rows, int a_base_offset, int b_shift_rows,
-                         int b_base_offset, int a_sbo, int b_sbo, void* stream);
+                         int b_base_offset, int a_sbo, int b_sbo, int a_lbo, int a_kstep, void* stream);
 
 #ifdef __cplusplus
 }
