@@ -43,7 +43,10 @@ struct Cfg {
     static constexpr int SMEM_BUDGET = 200 * 1024;
     static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for 32..256
+    // split precision stacks [B_hi ; B_lo] into ONE UMMA of N = 2*BLOCK_N (x_hi*w_hi and x_hi*w_lo land in adjacent column
+    // ranges, the epilogue adds them), so an accumulator is ACC_COLS = 2*BLOCK_N wide; two accumulators are in flight.
+    static constexpr int ACC_COLS = SPLIT ? 2 * BLOCK_N : BLOCK_N;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // power of two for 32..512
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -156,6 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_wide = make_idesc_bf16(BLOCK_M, 2 * BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -163,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -173,14 +177,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da_hi = make_smem_desc(a_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
                         const uint64_t db_hi = make_smem_desc(b_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
-                        umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (SPLIT) {
+                        if (!SPLIT) {
+                            umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        } else {
+                            // B_hi and B_lo are adjacent in the stage: the same descriptor with N = 2*BLOCK_N reads both.
+                            //   cols [0, N)   += x_hi * w_hi  (+ x_lo * w_hi from the second, N-wide UMMA)
+                            //   cols [N, 2N)  += x_hi * w_lo
+                            // 2 operand fetches of the A tile instead of 3 for the same three products.
                             const uint64_t da_lo =
                                 make_smem_desc(a_hi + C::A_BYTES + k * UMMA_K * 2, 16, 1024, kSwizzle128);
-                            const uint64_t db_lo =
-                                make_smem_desc(b_hi + C::B_BYTES + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                            umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (kb | k) != 0 ? 1u : 0u);
                             umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -223,13 +230,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + acc * BLOCK_N + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                tmem_ld_32x32(tmem_base + acc * C::ACC_COLS + c + (static_cast<uint32_t>(q * 32) << 16), v);
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    f[j] = __uint_as_float(v[j]);
-                    if (p.bias) f[j] += __ldg(p.bias + nblk * BLOCK_N + c + j);
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (SPLIT) {   // add the x_hi * w_lo half of the stacked accumulator
+                    tmem_ld_32x32(tmem_base + acc * C::ACC_COLS + BLOCK_N + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                }
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + nblk * BLOCK_N + c + j);
                 }
                 if (valid) {
                     if (arow) {
