@@ -325,7 +325,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     const long long pt_begin = ks * p.pt_per_split;
     long long pt_end = pt_begin + p.pt_per_split;
     if (pt_end > p.total_pt) pt_end = p.total_pt;
-    const uint32_t tmem_cols = npairs * 64 <= 64 ? 64 : npairs * 64 <= 128 ? 128 : npairs * 64 <= 256 ? 256 : 512;
+    // split precision: [dz_hi | dz_lo] is ONE N = 128 operand, so a tap pair owns 128 accumulator columns
+    constexpr int PAIR_COLS = SPLIT ? 128 : 64;
+    const uint32_t need_cols = npairs * PAIR_COLS;
+    const uint32_t tmem_cols = need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x_hi);
@@ -374,6 +377,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+            constexpr uint32_t idesc_wide = make_idesc_bf16(128, 128, 1, 1);
             const uint32_t sbo_a = static_cast<uint32_t>(p.halo_w) * 128u;   // 8-pixel groups follow the halo row pitch
             const uint32_t kstep_a = 2u * sbo_a;                            // UMMA K = 16 pixels = two tile rows
             int stage = 0;
@@ -395,17 +399,19 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                     const uint32_t off_a = static_cast<uint32_t>((ta / p.n_s) * p.halo_w + (ta % p.n_s) * p.s_step) * 128u;
                     const uint32_t off_b = static_cast<uint32_t>((tb / p.n_s) * p.halo_w + (tb % p.n_s) * p.s_step) * 128u;
                     const uint32_t lbo = off_b - off_a;
-                    const uint32_t d_tmem = tmem_base + pr * 64;
+                    const uint32_t d_tmem = tmem_base + pr * PAIR_COLS;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t da_hi = make_smem_desc(x_hi + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
+                        // dz_hi and dz_lo tiles are adjacent (LBO = G_BYTES): with N = 128 one UMMA yields x_hi*dz_hi in
+                        // columns [0,64) and x_hi*dz_lo in [64,128); the epilogue adds the halves.
                         const uint64_t db_hi = make_smem_desc(g_hi + k * 2048, G_BYTES, 1024, kSwizzle128);
-                        umma_f16(d_tmem, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
-                        if (SPLIT) {
+                        if (!SPLIT) {
+                            umma_f16(d_tmem, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
+                        } else {
                             const uint64_t da_lo = make_smem_desc(x_lo + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
-                            const uint64_t db_lo = make_smem_desc(g_lo + k * 2048, G_BYTES, 1024, kSwizzle128);
+                            umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (first && k == 0) ? 0u : 1u);
                             umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
                         }
                     }
                 }
@@ -437,14 +443,21 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
 #pragma unroll 1
             for (int c = 0; c < 64; c += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + pr * 64 + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                float f[32];
+                tmem_ld_32x32(tmem_base + pr * PAIR_COLS + c + (static_cast<uint32_t>(q * 32) << 16), v);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (SPLIT) {
+                    tmem_ld_32x32(tmem_base + pr * PAIR_COLS + 64 + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                }
                 if (live) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        atomicAdd(reinterpret_cast<float4*>(dst + c + j),
-                                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                              __uint_as_float(v[j + 3])));
+                        atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
                 }
             }
         }
@@ -507,8 +520,11 @@ static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, i
         hp.ws = static_cast<float*>(workspace);
         hp.N = N; hp.GH = GH; hp.GW = GW; hp.Cin_p = Cin_p; hp.Cout_p = Cout_p;
         hp.n_r = n_r; hp.n_s = n_s; hp.s_step = s_step; hp.h_off = h_off; hp.w_off = w_off;
-        hp.taps_per_group = H_MAX_TAPS;
-        hp.tap_groups = (n_r * n_s + H_MAX_TAPS - 1) / H_MAX_TAPS;
+        {   // tap groups: at most 512 TMEM columns per CTA (16 taps; 8 in split precision), groups balanced, each >= 2 taps
+            const int total = n_r * n_s, cap = split ? H_MAX_TAPS / 2 : H_MAX_TAPS;
+            hp.tap_groups = (total + cap - 1) / cap;
+            hp.taps_per_group = (total + hp.tap_groups - 1) / hp.tap_groups;
+        }
         hp.cchunks = Cin_p / 64; hp.n_blocks = Cout_p / 64;
         hp.tiles_h = ceil_div(GH, HP); hp.tiles_w = ceil_div(GW, HP);
         hp.total_pt = 1LL * N * hp.tiles_h * hp.tiles_w;
