@@ -120,7 +120,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // elect_one(), not `lane == 0`: with an elect.sync predicate ptxas issues the uniform-datapath instructions (UBLKCP,
+        // UTCHMMA) straight; a lane test makes it wrap each of them in an ELECT / BRA.U.ANY loop over the active lanes.
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -157,9 +159,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
             constexpr uint32_t idesc_wide = make_idesc_bf16(BLOCK_M, 2 * BLOCK_N, 0, 0);
+            const uint64_t dbase = desc_base(16, 1024, kSwizzle128);    // K-major, 128B swizzle, 8-row groups 1024 B apart
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -172,22 +175,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint32_t b_hi = a_hi + C::A_BYTES * C::PLANES;
+                    const uint64_t da_hi = dbase + (a_hi >> 4);
+                    const uint64_t da_lo = da_hi + (C::A_BYTES >> 4);
+                    const uint64_t db_hi = da_hi + ((C::A_BYTES * C::PLANES) >> 4);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da_hi = make_smem_desc(a_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
-                        const uint64_t db_hi = make_smem_desc(b_hi + k * UMMA_K * 2, 16, 1024, kSwizzle128);
+                        constexpr int KSTEP = (UMMA_K * 2) >> 4;      // 32 bytes along the 128-byte row, in 16-byte units
                         if (!SPLIT) {
-                            umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, da_hi + k * KSTEP, db_hi + k * KSTEP, idesc, (kb | k) != 0 ? 1u : 0u);
                         } else {
                             // B_hi and B_lo are adjacent in the stage: the same descriptor with N = 2*BLOCK_N reads both.
                             //   cols [0, N)   += x_hi * w_hi  (+ x_lo * w_hi from the second, N-wide UMMA)
                             //   cols [N, 2N)  += x_hi * w_lo
                             // 2 operand fetches of the A tile instead of 3 for the same three products.
-                            const uint64_t da_lo =
-                                make_smem_desc(a_hi + C::A_BYTES + k * UMMA_K * 2, 16, 1024, kSwizzle128);
-                            umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (kb | k) != 0 ? 1u : 0u);
-                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16(d_tmem, da_hi + k * KSTEP, db_hi + k * KSTEP, idesc_wide, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, da_lo + k * KSTEP, db_hi + k * KSTEP, idesc, 1u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire

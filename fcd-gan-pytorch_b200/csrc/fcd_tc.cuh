@@ -184,6 +184,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// Descriptor with the address field left at zero: `desc_base(...) + (saddr >> 4)` is the descriptor of the tile at shared
+// address saddr (< 256 KB, 16-byte aligned), so an issue loop only needs ONE 32-bit add per operand and UMMA.
+__device__ __forceinline__ uint64_t desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return make_smem_desc(0, lbo_bytes, sbo_bytes, layout);
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major (0 = K, 1 = MN)
 //   [16] B major           [17,23) N >> 3           [24,29) M >> 4

@@ -104,6 +104,88 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeParams p) {
     }
 }
 
+
+// ---- UMMA issue-rate micro-benchmark (scripts/umma_bench.py): how many cycles does a stream of tcgen05.mma with a given
+// shape / operand major-ness / descriptor geometry take when the operands are already in shared memory?
+struct BenchParams {
+    int mn_major, n1, n2;        // n2 == 0: one UMMA per k-step; else a second one (N = n2) with A at +a2_off
+    int a_sbo, a_lbo, a_kstep, a_shift, a2_off;
+    int b_sbo, b_lbo, b_kstep;
+    int stage_stride, stages, b_off;
+    int iters;
+    int a_tmem;                  // 1: A operand of the first UMMA comes from TMEM (columns 256..) instead of shared memory
+    long long* cycles;
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(BenchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_holder;
+    const int warp = threadIdx.x >> 5;
+    const int total = p.stage_stride * p.stages;
+    for (int i = threadIdx.x; i < total / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);       // small finite bf16 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_holder, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc1 = make_idesc_bf16(128, p.n1, p.mn_major, p.mn_major);
+        const uint32_t idesc2 = make_idesc_bf16(128, p.n2 ? p.n2 : 64, p.mn_major, p.mn_major);
+        const uint32_t base = smem_u32(smem);
+        // descriptors are built ONCE; the loop only adds 16-byte-unit offsets to the low word (address field)
+        const uint64_t da0 = make_smem_desc(base + p.a_shift * 128, p.a_lbo, p.a_sbo, kSwizzle128);
+        const uint64_t db0 = make_smem_desc(base + p.b_off, p.b_lbo, p.b_sbo, kSwizzle128);
+        const uint32_t a_k = p.a_kstep >> 4, b_k = p.b_kstep >> 4, a2 = p.a2_off >> 4, st = p.stage_stride >> 4;
+        const bool two = p.n2 != 0, ts = p.a_tmem != 0;
+        const long long t0 = clock64();
+        int stage = 0;
+        for (int it = 0; it < p.iters; ++it) {
+            const uint64_t da = da0 + static_cast<uint64_t>(stage * st);
+            const uint64_t db = db0 + static_cast<uint64_t>(stage * st);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ts) umma_f16_ts(tmem_base, tmem_base + 256 + k * 8, db + k * b_k, idesc1, 1u);
+                else umma_f16(tmem_base, da + k * a_k, db + k * b_k, idesc1, 1u);
+                if (two) umma_f16(tmem_base, da + a2 + k * a_k, db + k * b_k, idesc2, 1u);
+            }
+            if (++stage == p.stages) stage = 0;
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        p.cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 }  // namespace fcd
 
@@ -129,6 +211,22 @@ extern "C" int fcd_debug_umma_probe(const void* a, const void* b, float* d, int 
     FCD_CHECK_ARG(smem <= 200 * 1024, "umma_probe: operands do not fit shared memory");
     FCD_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     umma_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+extern "C" int fcd_debug_umma_bench(int mn_major, int n1, int n2, int a_sbo, int a_lbo, int a_kstep, int a_shift, int a2_off,
+                                    int b_sbo, int b_lbo, int b_kstep, int stage_stride, int stages, int b_off, int iters,
+                                    int a_tmem, int grid, long long* cycles, void* stream) {
+    FCD_CHECK_ARG(cycles && grid > 0 && iters > 0 && stages > 0, "umma_bench: bad arguments");
+    FCD_CHECK_ARG(stage_stride * stages <= 200 * 1024, "umma_bench: operands do not fit shared memory");
+    BenchParams p;
+    p.mn_major = mn_major; p.n1 = n1; p.n2 = n2;
+    p.a_sbo = a_sbo; p.a_lbo = a_lbo; p.a_kstep = a_kstep; p.a_shift = a_shift; p.a2_off = a2_off;
+    p.b_sbo = b_sbo; p.b_lbo = b_lbo; p.b_kstep = b_kstep;
+    p.stage_stride = stage_stride; p.stages = stages; p.b_off = b_off; p.iters = iters; p.a_tmem = a_tmem; p.cycles = cycles;
+    FCD_CUDA_OK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    umma_bench_kernel<<<grid, 128, stage_stride * stages + 2048, as_stream(stream)>>>(p);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

@@ -95,7 +95,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int tapv[2], cbv[2];
@@ -134,8 +134,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+            const uint64_t dbase = desc_base(SUB_BYTES, 1024, kSwizzle128);   // MN-major: LBO = distance between 64-wide blocks
             int stage = 0;
             uint32_t phase = 0;
             uint32_t first = 1;
@@ -143,17 +144,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-                const uint32_t b_hi = a_hi + C::A_BYTES * C::PLANES;
+                const uint64_t da_hi = dbase + (a_hi >> 4);
+                const uint64_t da_lo = da_hi + (C::A_BYTES >> 4);
+                const uint64_t db_hi = da_hi + ((C::A_BYTES * C::PLANES) >> 4);
+                const uint64_t db_lo = db_hi + (C::B_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t da_hi = make_smem_desc(a_hi + k * 2048, SUB_BYTES, 1024, kSwizzle128);
-                    const uint64_t db_hi = make_smem_desc(b_hi + k * 2048, SUB_BYTES, 1024, kSwizzle128);
-                    umma_f16(tmem_base, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
+                    constexpr int KSTEP = 2048 >> 4;          // 16 pixel rows of 128 bytes
+                    umma_f16(tmem_base, da_hi + k * KSTEP, db_hi + k * KSTEP, idesc, (first && k == 0) ? 0u : 1u);
                     if (SPLIT) {
-                        const uint64_t da_lo = make_smem_desc(a_hi + C::A_BYTES + k * 2048, SUB_BYTES, 1024, kSwizzle128);
-                        const uint64_t db_lo = make_smem_desc(b_hi + C::B_BYTES + k * 2048, SUB_BYTES, 1024, kSwizzle128);
-                        umma_f16(tmem_base, da_lo, db_hi, idesc, 1u);
-                        umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
+                        umma_f16(tmem_base, da_lo + k * KSTEP, db_hi + k * KSTEP, idesc, 1u);
+                        umma_f16(tmem_base, da_hi + k * KSTEP, db_lo + k * KSTEP, idesc, 1u);
                     }
                 }
                 first = 0;
@@ -283,6 +284,7 @@ static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CU
 constexpr int HP = 8;                 // K tile = HP x HP output pixels
 constexpr int H_MAX_TAPS = 16;        // 8 accumulators x 64 TMEM columns
 constexpr int H_SMEM_BUDGET = 200 * 1024;
+constexpr int H_MAX_GROUPS = 12;
 
 struct WHaloParams {
     float* ws;
@@ -293,9 +295,12 @@ struct WHaloParams {
     int x_bytes;              // bytes of one staged x plane (halo_w * halo_h * 128), slot rounded up to 1024
     int x_slot, stage_bytes, stages;
     int taps_per_group, tap_groups;
-    int cchunks, n_blocks, ksplit;
+    int cchunks, n_blocks;
     int tiles_h, tiles_w;
-    long long total_pt, pt_per_split;
+    long long total_pt;
+    // tap groups differ in their UMMA count (an odd group pads to a whole tap pair), so each group gets its own split-K
+    // factor, proportional to its pair count: every CTA then issues about the same number of UMMAs.
+    int ksplit_g[H_MAX_GROUPS], cta_start[H_MAX_GROUPS + 1];
 };
 
 template <bool SPLIT>
@@ -313,18 +318,22 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int item = blockIdx.x;
-    const int ks = item % p.ksplit; item /= p.ksplit;
-    const int nb = item % p.n_blocks; item /= p.n_blocks;
-    const int cb = item % p.cchunks;
-    const int tg = item / p.cchunks;
+    int tg = 0;
+    while (tg + 1 < p.tap_groups && static_cast<int>(blockIdx.x) >= p.cta_start[tg + 1]) ++tg;
+    int item = blockIdx.x - p.cta_start[tg];
+    const int ksplit = p.ksplit_g[tg];
+    const int ks = item % ksplit; item /= ksplit;
+    const int nb = item % p.n_blocks;
+    const int cb = item / p.n_blocks;
+    const long long pt_per_split = (p.total_pt + ksplit - 1) / ksplit;
     const int total_taps = p.n_r * p.n_s;
     const int tap0 = tg * p.taps_per_group;
     const int ntaps = (total_taps - tap0 < p.taps_per_group) ? total_taps - tap0 : p.taps_per_group;
     const int npairs = (ntaps + 1) >> 1;
-    const long long pt_begin = ks * p.pt_per_split;
-    long long pt_end = pt_begin + p.pt_per_split;
+    long long pt_begin = ks * pt_per_split;
+    long long pt_end = pt_begin + pt_per_split;
     if (pt_end > p.total_pt) pt_end = p.total_pt;
+    if (pt_begin > pt_end) pt_begin = pt_end;
     // split precision: [dz_hi | dz_lo] is ONE N = 128 operand, so a tap pair owns 128 accumulator columns
     constexpr int PAIR_COLS = SPLIT ? 128 : 64;
     const uint32_t need_cols = npairs * PAIR_COLS;
@@ -351,7 +360,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     const uint32_t stage_tx = static_cast<uint32_t>((p.x_bytes + G_BYTES) * PLANES);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long pt = pt_begin; pt < pt_end; ++pt) {
@@ -375,11 +384,29 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
             constexpr uint32_t idesc_wide = make_idesc_bf16(128, 128, 1, 1);
             const uint32_t sbo_a = static_cast<uint32_t>(p.halo_w) * 128u;   // 8-pixel groups follow the halo row pitch
-            const uint32_t kstep_a = 2u * sbo_a;                            // UMMA K = 16 pixels = two tile rows
+            const uint32_t kstep_a = (2u * sbo_a) >> 4;                     // UMMA K = 16 pixels = two tile rows (16-byte units)
+            // dz_hi and dz_lo tiles are adjacent (LBO = G_BYTES): with N = 128 one UMMA yields x_hi*dz_hi in columns [0,64)
+            // and x_hi*dz_lo in [64,128); the epilogue adds the halves.
+            const uint64_t dbase_b = desc_base(G_BYTES, 1024, kSwizzle128);
+            // per tap pair: the A descriptor (LBO = distance between the two tap views) relative to the staged x tile
+            uint64_t da_pair[H_MAX_TAPS / 2];
+#pragma unroll
+            for (int pr = 0; pr < H_MAX_TAPS / 2; ++pr) {
+                da_pair[pr] = 0;
+                if (pr >= npairs) continue;
+                int ta = tap0 + 2 * pr, tb = ta + 1;
+                if (tb >= tap0 + ntaps) {      // odd tap count: the last pair re-uses the previous tap as its first half
+                    tb = ta;
+                    ta = ta - 1;
+                }
+                const uint32_t off_a = static_cast<uint32_t>((ta / p.n_s) * p.halo_w + (ta % p.n_s) * p.s_step) * 128u;
+                const uint32_t off_b = static_cast<uint32_t>((tb / p.n_s) * p.halo_w + (tb % p.n_s) * p.s_step) * 128u;
+                da_pair[pr] = desc_base(off_b - off_a, sbo_a, kSwizzle128) + (off_a >> 4);
+            }
             int stage = 0;
             uint32_t phase = 0;
             uint32_t first = 1;
@@ -387,31 +414,20 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t x_hi = smem_u32(smem + stage * p.stage_bytes);
-                const uint32_t x_lo = x_hi + p.x_slot;
-                const uint32_t g_hi = x_hi + p.x_slot * PLANES;
-                const uint32_t g_lo = g_hi + G_BYTES;
-                for (int pr = 0; pr < npairs; ++pr) {
-                    int ta = tap0 + 2 * pr, tb = ta + 1;
-                    if (tb >= tap0 + ntaps) {      // odd tap count: the last pair re-uses the previous tap as its first half
-                        tb = ta;
-                        ta = ta - 1;
-                    }
-                    const uint32_t off_a = static_cast<uint32_t>((ta / p.n_s) * p.halo_w + (ta % p.n_s) * p.s_step) * 128u;
-                    const uint32_t off_b = static_cast<uint32_t>((tb / p.n_s) * p.halo_w + (tb % p.n_s) * p.s_step) * 128u;
-                    const uint32_t lbo = off_b - off_a;
+                const uint32_t xs = x_hi >> 4, xl = (x_hi + p.x_slot) >> 4;
+                const uint64_t db_hi = dbase_b + ((x_hi + p.x_slot * PLANES) >> 4);
+#pragma unroll
+                for (int pr = 0; pr < H_MAX_TAPS / 2; ++pr) {
+                    if (pr >= npairs) break;
                     const uint32_t d_tmem = tmem_base + pr * PAIR_COLS;
+                    const uint64_t da_hi = da_pair[pr] + xs, da_lo = da_pair[pr] + xl;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t da_hi = make_smem_desc(x_hi + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
-                        // dz_hi and dz_lo tiles are adjacent (LBO = G_BYTES): with N = 128 one UMMA yields x_hi*dz_hi in
-                        // columns [0,64) and x_hi*dz_lo in [64,128); the epilogue adds the halves.
-                        const uint64_t db_hi = make_smem_desc(g_hi + k * 2048, G_BYTES, 1024, kSwizzle128);
                         if (!SPLIT) {
-                            umma_f16(d_tmem, da_hi, db_hi, idesc, (first && k == 0) ? 0u : 1u);
+                            umma_f16(d_tmem, da_hi + k * kstep_a, db_hi + k * (2048 >> 4), idesc, (first && k == 0) ? 0u : 1u);
                         } else {
-                            const uint64_t da_lo = make_smem_desc(x_lo + off_a + k * kstep_a, lbo, sbo_a, kSwizzle128);
-                            umma_f16(d_tmem, da_hi, db_hi, idesc_wide, (first && k == 0) ? 0u : 1u);
-                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16(d_tmem, da_hi + k * kstep_a, db_hi + k * (2048 >> 4), idesc_wide, (first && k == 0) ? 0u : 1u);
+                            umma_f16(d_tmem, da_lo + k * kstep_a, db_hi + k * (2048 >> 4), idesc, 1u);
                         }
                     }
                 }
@@ -523,18 +539,36 @@ static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, i
         {   // tap groups: at most 512 TMEM columns per CTA (16 taps; 8 in split precision), groups balanced, each >= 2 taps
             const int total = n_r * n_s, cap = split ? H_MAX_TAPS / 2 : H_MAX_TAPS;
             hp.tap_groups = (total + cap - 1) / cap;
+            FCD_CHECK_ARG(hp.tap_groups <= H_MAX_GROUPS, "conv2d_wgrad_tc: too many taps (%d)", total);
             hp.taps_per_group = (total + hp.tap_groups - 1) / hp.tap_groups;
         }
         hp.cchunks = Cin_p / 64; hp.n_blocks = Cout_p / 64;
         hp.tiles_h = ceil_div(GH, HP); hp.tiles_w = ceil_div(GW, HP);
         hp.total_pt = 1LL * N * hp.tiles_h * hp.tiles_w;
-        const long long base = 1LL * hp.cchunks * hp.n_blocks * hp.tap_groups;
+        // CTA budget: one wave (1 CTA per SM is resident).  Each (cb, nb) block gets `slots` CTAs, shared between the tap
+        // groups in proportion to their tap-pair counts.
+        const long long mn_blocks = 1LL * hp.cchunks * hp.n_blocks;
         const long long sms = sm_count();
-        long long ks = base >= sms ? 1 : sms / base;          // fill one wave (1 CTA per SM is resident)
-        if (ks > hp.total_pt) ks = hp.total_pt;
-        if (ks < 1) ks = 1;
-        hp.pt_per_split = (hp.total_pt + ks - 1) / ks;
-        hp.ksplit = static_cast<int>((hp.total_pt + hp.pt_per_split - 1) / hp.pt_per_split);
+        int pairs_g[H_MAX_GROUPS], pairs_total = 0;
+        for (int g = 0; g < hp.tap_groups; ++g) {
+            const int t0 = g * hp.taps_per_group;
+            const int nt = (n_r * n_s - t0 < hp.taps_per_group) ? n_r * n_s - t0 : hp.taps_per_group;
+            pairs_g[g] = (nt + 1) / 2;
+            pairs_total += pairs_g[g];
+        }
+        long long slots = sms / mn_blocks;
+        if (slots < hp.tap_groups) slots = hp.tap_groups;
+        unsigned grid = 0;
+        for (int g = 0; g < hp.tap_groups; ++g) {
+            long long ks = (slots * pairs_g[g] + pairs_total / 2) / pairs_total;
+            if (ks < 1) ks = 1;
+            if (ks > hp.total_pt) ks = hp.total_pt;
+            const long long per = (hp.total_pt + ks - 1) / ks;
+            hp.ksplit_g[g] = static_cast<int>((hp.total_pt + per - 1) / per);
+            hp.cta_start[g] = static_cast<int>(grid);
+            grid += static_cast<unsigned>(hp.ksplit_g[g] * mn_blocks);
+        }
+        hp.cta_start[hp.tap_groups] = static_cast<int>(grid);
         CUtensorMap mxh, mxl, mgh, mgl;
         int rc;
         if ((rc = make_act_tmap(&mxh, x_hi, Cin_p, XW, XH, N, x_ld, 64, hp.halo_w, hp.halo_h, 1, 1))) return rc;
@@ -547,7 +581,6 @@ static int wgrad_tc_core(const void* x_hi, const void* x_lo, int x_ld, int XH, i
             mgl = mgh;
         }
         FCD_CUDA_OK(cudaMemsetAsync(workspace, 0, need, stream));
-        const unsigned grid = static_cast<unsigned>(base * hp.ksplit);
         rc = split ? launch_wgrad_halo<true>(mxh, mxl, mgh, mgl, hp, grid, stream)
                    : launch_wgrad_halo<false>(mxh, mxl, mgh, mgl, hp, grid, stream);
         if (rc) return rc;

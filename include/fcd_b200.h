@@ -251,6 +251,12 @@ int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int
                          int mn_major, int n, int ksteps, int a_shift_rows, int a_base_offset, int b_shift_rows,
                          int b_base_offset, int a_sbo, int b_sbo, int a_lbo, int a_kstep, void* stream);
 
+/* tcgen05.mma issue-rate micro-benchmark (scripts/umma_bench.py): cycles for `iters` x 4 k-steps of UMMA(s) with the given
+ * shape / major-ness / descriptor geometry, operands resident in shared memory; cycles[grid].  Not on the product path. */
+int fcd_debug_umma_bench(int mn_major, int n1, int n2, int a_sbo, int a_lbo, int a_kstep, int a_shift, int a2_off, int b_sbo,
+                         int b_lbo, int b_kstep, int stage_stride, int stages, int b_off, int iters, int a_tmem, int grid,
+                         long long* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
