@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <initializer_list>
+
 #include "fcd_common.cuh"
 #include "fcd_tc.cuh"
 
@@ -296,6 +298,293 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     }
 }
 
+
+// =====================================================================================================================
+// Halo-reuse convolution (stride-1 reads): conv_tc_kernel re-fetches the input tile once per tap (9 x 32 KB per 128 output
+// pixels of a 3x3 layer in split precision) and is bound by the L2 -> SM fabric (ncu: lts 59 %, tensor pipe 41 %).  Here
+//   * the packed weights of the CTA's output-channel block ([tap][k-chunk][w_hi ; w_lo], <= ~150 KB) are loaded into shared
+//     memory ONCE per CTA and stay resident for all of its pixel tiles;
+//   * per pixel tile (16 rows x 8 pixels = M 128) the input is staged once WITH its halo (TMA box {64 ch, 8 + (n_s-1)|dw|,
+//     16 + (n_r-1)|dh|}); every tap's A operand is a ROW-SHIFTED VIEW of that staged tile: K-major descriptor, start address
+//     moved by (r * halo_w + s) pixels, stride-byte-offset = halo_w * 128 so the 8-pixel groups follow the halo row pitch
+//     (semantics pinned on the device by scripts/probe_halo.py);
+//   * split precision stages the hi and lo planes as separate ring items: all taps of x_hi * [w_hi ; w_lo] (N = 2*BLOCK_N),
+//     then all taps of x_lo * w_hi (N = BLOCK_N), so three plane slots are enough for a one-tile look-ahead.
+// L2 -> shared traffic per pixel tile drops from taps * 48 KB to 2 * 23 KB for a 3x3 64->64 layer.
+// The BatchNorm statistics are accumulated in registers across the CTA's tiles (butterfly column sums, fp32 per 32 pixels,
+// double across tiles) and flushed with one double atomic per (warp, channel) at the end.
+// =====================================================================================================================
+constexpr int HT_H = 16, HT_W = 8;      // pixel tile of the halo kernel (M = 128 = 16 groups of 8 pixels)
+
+struct ConvHaloParams {
+    ConvTcParams c;
+    int halo_w, halo_h;      // staged box, pixels
+    int x_bytes, slot_bytes; // bytes of one staged plane; slot = x_bytes rounded up to 1024
+    int nslots, w_bytes;     // x ring depth; resident weight bytes (taps * cchunks * PLANES * BLOCK_N * 128)
+    int box_dh, box_dw;      // box origin relative to the tile's first output pixel
+    int off_h0, off_w0;      // in-box position of tap (0, 0)
+    long long pix_tiles;     // N * tiles_h * tiles_w
+};
+
+// column sums over the 32 lanes of a warp: on return lane l holds sum_over_lanes v[l]  (31 shuffles; v is destroyed)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const ConvHaloParams hp) {
+    constexpr int PLANES = SPLIT ? 2 : 1;
+    constexpr int WT_BYTES = BLOCK_N * 128;                  // one (tap, k-chunk) weight tile of one plane
+    constexpr int ACC_COLS = SPLIT ? 2 * BLOCK_N : BLOCK_N;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    constexpr int MAX_SLOTS = 8;
+    const ConvTcParams& p = hp.c;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* wsm = smem;
+    uint8_t* xsm = smem + hp.w_bytes;                        // w_bytes is a multiple of 1024
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(xsm + hp.nslots * hp.slot_bytes);
+    uint64_t* empty_bar = full_bar + MAX_SLOTS;
+    uint64_t* tmem_full = empty_bar + MAX_SLOTS;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* w_bar = tmem_empty + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nblk = blockIdx.x % p.n_blocks;
+    const long long tile0 = blockIdx.x / p.n_blocks, tile_step = gridDim.x / p.n_blocks;
+    const int cchunks = p.Cin_p / BLOCK_K;
+    const int ntaps = p.n_r * p.n_s;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x_hi);
+        tma_prefetch_desc(&map_w_hi);
+        if (SPLIT) {
+            tma_prefetch_desc(&map_x_lo);
+            tma_prefetch_desc(&map_w_lo);
+        }
+        for (int i = 0; i < hp.nslots; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        mbar_init(w_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            // resident weights: [tap][k-chunk][plane][BLOCK_N rows x 128 B]
+            mbar_expect_tx(w_bar, static_cast<uint32_t>(hp.w_bytes));
+            for (int t = 0; t < ntaps; ++t) {
+                const int ti = t / p.n_s, tj = t - ti * p.n_s;
+                const int tap = (p.w_r0 + ti * p.w_rstep) * p.KW + (p.w_s0 + tj * p.w_sstep);
+                for (int cc = 0; cc < cchunks; ++cc) {
+                    uint8_t* dst = wsm + static_cast<size_t>(t * cchunks + cc) * PLANES * WT_BYTES;
+                    tma_load_3d(dst, &map_w_hi, w_bar, cc * BLOCK_K, nblk * BLOCK_N, tap);
+                    if (SPLIT) tma_load_3d(dst + WT_BYTES, &map_w_lo, w_bar, cc * BLOCK_K, nblk * BLOCK_N, tap);
+                }
+            }
+            int slot = 0;
+            uint32_t phase = 0;
+            for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
+                long long t = tile;
+                const int tw = static_cast<int>(t % p.tiles_w);
+                t /= p.tiles_w;
+                const int th = static_cast<int>(t % p.tiles_h);
+                const int n = static_cast<int>(t / p.tiles_h);
+                const int h0 = th * HT_H + hp.box_dh, w0 = tw * HT_W + hp.box_dw;
+                for (int cc = 0; cc < cchunks; ++cc) {
+#pragma unroll
+                    for (int pl = 0; pl < PLANES; ++pl) {
+                        mbar_wait(&empty_bar[slot], phase ^ 1u);
+                        mbar_expect_tx(&full_bar[slot], static_cast<uint32_t>(hp.x_bytes));
+                        tma_load_4d(xsm + slot * hp.slot_bytes, pl ? &map_x_lo : &map_x_hi, &full_bar[slot], cc * BLOCK_K, w0,
+                                    h0, n);
+                        if (++slot == hp.nslots) {
+                            slot = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_wide = make_idesc_bf16(BLOCK_M, 2 * BLOCK_N, 0, 0);
+            constexpr int KSTEP = (UMMA_K * 2) >> 4;
+            const uint64_t dbase_a = desc_base(16, static_cast<uint32_t>(hp.halo_w) * 128u, kSwizzle128);
+            const uint64_t dbase_b = desc_base(16, 1024, kSwizzle128) + (smem_u32(wsm) >> 4);
+            const uint32_t xs0 = smem_u32(xsm) >> 4;
+            mbar_wait(w_bar, 0);
+            int slot = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int cc = 0; cc < cchunks; ++cc) {
+#pragma unroll
+                    for (int pl = 0; pl < PLANES; ++pl) {
+                        mbar_wait(&full_bar[slot], phase);
+                        tc_fence_after();
+                        const uint64_t da0 = dbase_a + (xs0 + ((slot * hp.slot_bytes) >> 4));
+                        uint32_t toff_row = static_cast<uint32_t>(hp.off_h0 * hp.halo_w + hp.off_w0) * 8u;   // 128 B = 8 units
+                        uint32_t woff = static_cast<uint32_t>(cc * PLANES * WT_BYTES) >> 4;
+                        for (int ti = 0; ti < p.n_r; ++ti) {
+                            uint32_t toff = toff_row;
+                            for (int tj = 0; tj < p.n_s; ++tj) {
+                                const uint64_t da = da0 + toff;
+                                const uint64_t db = dbase_b + woff;
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                    if (pl == 0)
+                                        umma_f16(d_tmem, da + k * KSTEP, db + k * KSTEP, SPLIT ? idesc_wide : idesc,
+                                                 (cc | ti | tj | k) != 0 ? 1u : 0u);
+                                    else
+                                        umma_f16(d_tmem, da + k * KSTEP, db + k * KSTEP, idesc, 1u);
+                                }
+                                toff += static_cast<uint32_t>(p.dw_step * 8);
+                                woff += static_cast<uint32_t>(cchunks * PLANES * WT_BYTES) >> 4;
+                            }
+                            toff_row += static_cast<uint32_t>(p.dh_step * hp.halo_w * 8);
+                        }
+                        umma_commit(&empty_bar[slot]);      // frees the plane slot when these MMAs retire
+                        if (++slot == hp.nslots) {
+                            slot = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int lh = row / HT_W, lw = row - lh * HT_W;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        double st_sum[BLOCK_N / 32], st_sq[BLOCK_N / 32];
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 32; ++i) st_sum[i] = st_sq[i] = 0.0;
+        const float* bias = p.bias ? p.bias + nblk * BLOCK_N : nullptr;
+        for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
+            long long t = tile;
+            const int tw = static_cast<int>(t % p.tiles_w);
+            t /= p.tiles_w;
+            const int th = static_cast<int>(t % p.tiles_h);
+            const int n = static_cast<int>(t / p.tiles_h);
+            const int oh_l = th * HT_H + lh, ow_l = tw * HT_W + lw;
+            const bool valid = (oh_l < p.TOH) && (ow_l < p.TOW);
+            const int oh = oh_l * p.out_sh + p.out_oh, ow = ow_l * p.out_sw + p.out_ow;
+            const size_t pix = static_cast<size_t>(n) * p.OH * p.OW + static_cast<size_t>(oh) * p.OW + ow;
+            float* zrow = p.z + pix * p.z_ld + nblk * BLOCK_N;
+            const float* arow = p.addend ? p.addend + pix * p.addend_ld + nblk * BLOCK_N : nullptr;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
+                const int c = ci * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + acc * ACC_COLS + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (SPLIT) {   // add the x_hi * w_lo half of the stacked accumulator
+                    tmem_ld_32x32(tmem_base + acc * ACC_COLS + BLOCK_N + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                }
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c + j);
+                }
+                if (valid) {
+                    if (arow) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 a = *reinterpret_cast<const float4*>(arow + c + j);
+                            f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(zrow + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+                if (p.stat_sum) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = valid ? f[j] : 0.f;
+                        sq[j] = f[j] * f[j];
+                    }
+                    st_sum[ci] += static_cast<double>(warp_colsum32(f, lane));
+                    st_sq[ci] += static_cast<double>(warp_colsum32(sq, lane));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        if (p.stat_sum) {
+#pragma unroll
+            for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
+                atomicAdd(p.stat_sum + nblk * BLOCK_N + ci * 32 + lane, st_sum[ci]);
+                atomicAdd(p.stat_sqsum + nblk * BLOCK_N + ci * 32 + lane, st_sq[ci]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -367,6 +656,68 @@ bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
     return (stride == 1 || stride == 2) && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH >= 1 && KW >= 1 && KH <= 9 && KW <= 9;
 }
 
+
+bool g_conv_halo_enabled = true;    // fcd_set_option("conv_halo", 0) selects the per-tap kernel everywhere
+
+namespace {
+constexpr int HALO_SMEM_MAX = 227 * 1024 - 1024;   // opt-in limit minus the kernel's static shared memory
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
+                            const ConvHaloParams& hp, int smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FCD_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HALO_SMEM_MAX));
+        attr_set = true;
+    }
+    long long grid = sm_count() / hp.c.n_blocks * hp.c.n_blocks;
+    if (grid < hp.c.n_blocks) grid = hp.c.n_blocks;
+    if (grid > hp.pix_tiles * hp.c.n_blocks) grid = hp.pix_tiles * hp.c.n_blocks;
+    conv_halo_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mwh, mwl, hp);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+// Fills hp and returns true when the halo kernel takes this launch: stride-1 reads, every tap view inside one TMA box, and the
+// CTA's weight block resident in shared memory next to >= 3 (split) / 2 plane slots.
+static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, int* block_n_out, ConvHaloParams* hp,
+                           int* smem_bytes) {
+    if (!g_conv_halo_enabled || csh != 1 || csw != 1 || p.n_r * p.n_s < 2) return false;
+    const int span_h = (p.n_r - 1) * (p.dh_step < 0 ? -p.dh_step : p.dh_step);
+    const int span_w = (p.n_s - 1) * (p.dw_step < 0 ? -p.dw_step : p.dw_step);
+    const int halo_h = HT_H + span_h, halo_w = HT_W + span_w;
+    if (halo_h > 256 || halo_w > 256) return false;
+    const int x_bytes = halo_h * halo_w * 128;
+    const int slot = (x_bytes + 1023) & ~1023;
+    const int planes = split ? 2 : 1;
+    const int cchunks = p.Cin_p / BLOCK_K;
+    const int min_slots = split ? 3 : 2;
+    int block_n = 0, nslots = 0, w_bytes = 0;
+    for (int bn : {128, 64}) {
+        if (p.Cout_p % bn) continue;
+        if (split && bn == 128) continue;                      // 2 * (2 * 128) accumulator columns would need all of TMEM
+        const long long wb = 1LL * p.n_r * p.n_s * cchunks * planes * bn * 128;
+        const long long room = HALO_SMEM_MAX - 1024 - 256 - wb;
+        if (room < 1LL * min_slots * slot) continue;
+        block_n = bn; w_bytes = static_cast<int>(wb);
+        nslots = static_cast<int>(room / slot);
+        if (nslots > 8) nslots = 8;
+        break;
+    }
+    if (!block_n) return false;
+    hp->c = p;
+    hp->halo_w = halo_w; hp->halo_h = halo_h; hp->x_bytes = x_bytes; hp->slot_bytes = slot; hp->nslots = nslots;
+    hp->w_bytes = w_bytes;
+    const int min_dh = p.dh_step < 0 ? (p.n_r - 1) * p.dh_step : 0, min_dw = p.dw_step < 0 ? (p.n_s - 1) * p.dw_step : 0;
+    hp->box_dh = p.dh0 + min_dh; hp->box_dw = p.dw0 + min_dw;
+    hp->off_h0 = -min_dh; hp->off_w0 = -min_dw;
+    *block_n_out = block_n;
+    *smem_bytes = w_bytes + nslots * slot + 1024 + 256;
+    return true;
+}
+
 template <int BLOCK_N, bool SPLIT>
 static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh,
                           const CUtensorMap& mwl, const ConvTcParams& p, cudaStream_t stream) {
@@ -386,9 +737,39 @@ static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const 
 static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int XW, const void* w_hi, const void* w_lo,
                        int w_rows, int w_cols, int w_taps, ConvTcParams p, int N, int csh, int csw, cudaStream_t stream) {
     const bool split = (x_lo != nullptr) && (w_lo != nullptr);
-    const int block_n = (p.Cout_p % 128 == 0) ? 128 : 64;
     CUtensorMap mxh, mxl, mwh, mwl;
     int rc;
+    {
+        ConvHaloParams hp;
+        int hbn = 0, hsmem = 0;
+        if (conv_halo_plan(p, split, csh, csw, &hbn, &hp, &hsmem)) {
+            if ((rc = make_act_tmap(&mxh, x_hi, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, hp.halo_w, hp.halo_h, 1, 1))) return rc;
+            if ((rc = make_wgt_tmap(&mwh, w_hi, w_cols, w_rows, w_taps, BLOCK_K, hbn))) return rc;
+            if (split) {
+                if ((rc = make_act_tmap(&mxl, x_lo, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, hp.halo_w, hp.halo_h, 1, 1))) return rc;
+                if ((rc = make_wgt_tmap(&mwl, w_lo, w_cols, w_rows, w_taps, BLOCK_K, hbn))) return rc;
+            } else {
+                mxl = mxh;
+                mwl = mwh;
+            }
+            hp.c.N = N; hp.c.csh = 1; hp.c.csw = 1;
+            hp.c.tiles_h = ceil_div(p.TOH, HT_H);
+            hp.c.tiles_w = ceil_div(p.TOW, HT_W);
+            hp.c.n_blocks = p.Cout_p / hbn;
+            hp.pix_tiles = 1LL * N * hp.c.tiles_h * hp.c.tiles_w;
+            hp.c.total_tiles = hp.pix_tiles * hp.c.n_blocks;
+            if (hbn == 128) return launch_conv_halo<128, false>(mxh, mxl, mwh, mwl, hp, hsmem, stream);
+            return split ? launch_conv_halo<64, true>(mxh, mxl, mwh, mwl, hp, hsmem, stream)
+                         : launch_conv_halo<64, false>(mxh, mxl, mwh, mwl, hp, hsmem, stream);
+        }
+    }
+    const int block_n = (p.Cout_p % 128 == 0) ? 128 : 64;
+    // the per-tap kernel's in-epilogue statistics cost two double atomics per (warp, channel, tile): run the dedicated
+    // reduction kernel after it instead
+    double* stat_sum = p.stat_sum;
+    double* stat_sqsum = p.stat_sqsum;
+    p.stat_sum = nullptr;
+    p.stat_sqsum = nullptr;
     if ((rc = make_act_tmap(&mxh, x_hi, p.Cin_p, XW, XH, N, x_ld, BLOCK_K, TILE_W, TILE_H, csw, csh))) return rc;
     if ((rc = make_wgt_tmap(&mwh, w_hi, w_cols, w_rows, w_taps, BLOCK_K, block_n))) return rc;
     if (split) {
@@ -406,10 +787,15 @@ static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int
     p.n_blocks = p.Cout_p / block_n;
     p.total_tiles = 1LL * N * p.tiles_h * p.tiles_w * p.n_blocks;
     if (block_n == 128)
-        return split ? launch_conv_tc<128, true>(mxh, mxl, mwh, mwl, p, stream)
-                     : launch_conv_tc<128, false>(mxh, mxl, mwh, mwl, p, stream);
-    return split ? launch_conv_tc<64, true>(mxh, mxl, mwh, mwl, p, stream)
-                 : launch_conv_tc<64, false>(mxh, mxl, mwh, mwl, p, stream);
+        rc = split ? launch_conv_tc<128, true>(mxh, mxl, mwh, mwl, p, stream)
+                   : launch_conv_tc<128, false>(mxh, mxl, mwh, mwl, p, stream);
+    else
+        rc = split ? launch_conv_tc<64, true>(mxh, mxl, mwh, mwl, p, stream)
+                   : launch_conv_tc<64, false>(mxh, mxl, mwh, mwl, p, stream);
+    if (rc) return rc;
+    if (stat_sum)
+        return fcd_bn_stats(p.z, p.z_ld, 1LL * N * p.OH * p.OW, p.Cout_p, stat_sum, stat_sqsum, stream);
+    return FCD_OK;
 }
 
 int conv2d_fwd_tc(const void* x_hi, const void* x_lo, int x_ld, const void* w_hi, const void* w_lo,

@@ -28,7 +28,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
 BN_MOMENTUM = 0.1
 
-_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": False}
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True}
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_*.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
