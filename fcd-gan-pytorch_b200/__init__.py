@@ -3,6 +3,7 @@ nn.Module call surface.  Import as `fcdgan_b200`.
 
     from fcdgan_b200 import Generator, Segmentor, Discriminator_SRGAN_simple      # Module.py
     from fcdgan_b200 import CNetLoss, CGeneratorLoss, region_loss, MS_SSIM, SSIM  # Loss.py / ssim.py
+    from fcdgan_b200 import usss_step, rsss_step, wsss_step                       # Demo_*.py loop bodies
 
 Everything numerical runs in hand-written sm_100a CUDA (libfcd_b200.so, C ABI in include/fcd_b200.h); there is
 no CPU fallback — constructing modules works anywhere, calling them needs a B200 and the built library.
@@ -15,3 +16,4 @@ from .modules import (DoubleConv, Discriminator_SRGAN_simple, Down, Generator, O
 from .losses import (CGeneratorLoss, CNetLoss, PerceptionLoss, mean, mean_abs, mean_sq, region_loss,  # noqa: F401
                      soft_mask)
 from .ssim import MS_SSIM, SSIM, ms_ssim, ssim  # noqa: F401
+from .steps import rsss_step, usss_step, wsss_step  # noqa: F401

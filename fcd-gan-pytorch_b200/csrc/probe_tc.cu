@@ -186,6 +186,102 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(BenchParams p) {
     }
 }
 
+
+// ---- UMMA "program" benchmark (scripts/umma_bench2.py): per k-step issue a fixed, COMPILE-TIME list of UMMAs (entry = N,
+// A offset, B offset, accumulator column), fully unrolled with immediate descriptor offsets, so the issue thread spends
+// ~2 instructions per UMMA and the measured cycles are the tensor pipe's, not the issue loop's.
+struct PEntry { int n, a, b, d; };
+constexpr int PKB = 1024;
+constexpr int PB0 = 128 * PKB, PB1 = 160 * PKB;      // B tiles (32 KB each, up to N = 256); A tiles are 16 KB apart from 0
+#define PA(i) ((i) * 16 * PKB)
+constexpr int NPROG = 20;
+__device__ constexpr int PCNT[NPROG] = {1, 2, 2, 4, 2, 2, 2, 2, 4, 4, 8, 1, 2, 3, 4, 1, 4, 2, 4, 2};
+__device__ constexpr PEntry PROGS[NPROG][8] = {
+    /* 0 */ {{128, PA(0), PB0, 0}},
+    /* 1 */ {{128, PA(0), PB0, 0}, {128, PA(1), PB0, 0}},                                   // same B, same accumulator
+    /* 2 */ {{128, PA(0), PB0, 0}, {128, PA(1), PB0, 128}},                                 // same B, separate accumulators
+    /* 3 */ {{128, PA(0), PB0, 0}, {128, PA(1), PB0, 128}, {128, PA(2), PB0, 256}, {128, PA(3), PB0, 384}},
+    /* 4 */ {{128, PA(0), PB0, 0}, {128, PA(0), PB1, 128}},                                 // same A
+    /* 5 */ {{128, PA(0), PB0, 0}, {128, PA(1), PB1, 128}},                                 // nothing shared
+    /* 6 */ {{128, PA(0), PB0, 0}, {64, PA(1), PB0, 0}},                                    // split pair, current order
+    /* 7 */ {{128, PA(0), PB0, 0}, {64, PA(1), PB0, 128}},
+    /* 8 */ {{128, PA(0), PB0, 0}, {128, PA(2), PB0, 128}, {64, PA(1), PB0, 0}, {64, PA(3), PB0, 128}},   // 2 tiles hi,hi,lo,lo
+    /* 9 */ {{128, PA(0), PB0, 0}, {64, PA(1), PB0, 0}, {128, PA(2), PB0, 128}, {64, PA(3), PB0, 128}},   // 2 tiles hi,lo,hi,lo
+    /*10 */ {{128, PA(0), PB0, 0}, {128, PA(2), PB0, 128}, {128, PA(4), PB0, 256}, {128, PA(6), PB0, 384},
+             {64, PA(1), PB0, 0}, {64, PA(3), PB0, 128}, {64, PA(5), PB0, 256}, {64, PA(7), PB0, 384}},
+    /*11 */ {{256, PA(0), PB0, 0}},
+    /*12 */ {{256, PA(0), PB0, 0}, {256, PA(1), PB0, 256}},
+    /*13 */ {{64, PA(0), PB0, 0}, {64, PA(1), PB0, 0}, {64, PA(0), PB0 + 8 * PKB, 0}},       // unstacked split
+    /*14 */ {{64, PA(0), PB0, 0}, {64, PA(1), PB0, 64}, {64, PA(2), PB0, 128}, {64, PA(3), PB0, 192}},
+    /*15 */ {{64, PA(0), PB0, 0}},
+    /*16 */ {{256, PA(0), PB0, 0}, {256, PA(1), PB0, 256}, {256, PA(2), PB0, 0}, {256, PA(3), PB0, 256}},
+    /*17 */ {{64, PA(0), PB0, 0}, {64, PA(1), PB1, 64}},                                    // N=64, nothing shared
+    /*18 */ {{128, PA(0), PB0, 0}, {128, PA(1), PB1, 128}, {128, PA(2), PB0, 256}, {128, PA(3), PB1, 384}},   // nothing shared x4
+    /*19 */ {{192, PA(0), PB0, 0}, {192, PA(1), PB0, 192}},
+};
+
+template <int P>
+__device__ __forceinline__ void run_prog(uint32_t base16, uint32_t tmem_base, uint32_t hi_word, int iters) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int i = 0; i < PCNT[P]; ++i) {
+                const uint32_t a_lo = base16 + ((PROGS[P][i].a + k * 32) >> 4) + (1u << 16);    // LBO field = 1 (16 bytes)
+                const uint32_t b_lo = base16 + ((PROGS[P][i].b + k * 32) >> 4) + (1u << 16);
+                const uint64_t da = (static_cast<uint64_t>(hi_word) << 32) | a_lo;
+                const uint64_t db = (static_cast<uint64_t>(hi_word) << 32) | b_lo;
+                umma_f16(tmem_base + PROGS[P][i].d, da, db, make_idesc_bf16(128, PROGS[P][i].n, 0, 0), 1u);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) umma_prog_kernel(int prog, int iters, int a_sbo, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_holder;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 192 * PKB / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_holder, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+    if (warp == 0 && elect_one()) {
+        const uint32_t base16 = smem_u32(smem) >> 4;
+        const uint32_t hi_word = static_cast<uint32_t>(make_smem_desc(0, 0, a_sbo, kSwizzle128) >> 32);
+        const long long t0 = clock64();
+        switch (prog) {
+#define PCASE(P) case P: run_prog<P>(base16, tmem_base, hi_word, iters); break;
+            PCASE(0) PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
+            PCASE(12) PCASE(13) PCASE(14) PCASE(15) PCASE(16) PCASE(17) PCASE(18) PCASE(19)
+#undef PCASE
+            default: break;
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 }  // namespace fcd
 
@@ -227,6 +323,14 @@ extern "C" int fcd_debug_umma_bench(int mn_major, int n1, int n2, int a_sbo, int
     p.stage_stride = stage_stride; p.stages = stages; p.b_off = b_off; p.iters = iters; p.a_tmem = a_tmem; p.cycles = cycles;
     FCD_CUDA_OK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     umma_bench_kernel<<<grid, 128, stage_stride * stages + 2048, as_stream(stream)>>>(p);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+extern "C" int fcd_debug_umma_prog(int prog, int iters, int a_sbo, int grid, long long* cycles, void* stream) {
+    FCD_CHECK_ARG(prog >= 0 && prog < NPROG && iters > 0 && grid > 0 && cycles, "umma_prog: bad arguments");
+    FCD_CUDA_OK(cudaFuncSetAttribute(umma_prog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    umma_prog_kernel<<<grid, 128, 194 * 1024, as_stream(stream)>>>(prog, iters, a_sbo, cycles);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

@@ -257,6 +257,9 @@ int fcd_debug_umma_bench(int mn_major, int n1, int n2, int a_sbo, int a_lbo, int
                          int b_lbo, int b_kstep, int stage_stride, int stages, int b_off, int iters, int a_tmem, int grid,
                          long long* cycles, void* stream);
 
+/* compile-time UMMA "programs" (operand-reuse experiments, scripts/umma_bench2.py; the list is in probe_tc.cu) */
+int fcd_debug_umma_prog(int prog, int iters, int a_sbo, int grid, long long* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

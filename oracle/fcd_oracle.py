@@ -383,3 +383,28 @@ def rsss_s_loss(sdG: SD, sdD: SD, x: Tensor, y: Tensor, region: Tensor, cmap: Te
     l1 = region_loss(cmap, region, "l1")
     r = region_loss(cmap, 1 - region, "mse")
     return d_weight * c_out.mean() + l1_weight * l1 + g_weight * g_loss + r_weight * r
+
+
+def wsss_d_loss(sdS: SD, sdD: SD, x: Tensor, y: Tensor, x_nc: Tensor, y_nc: Tensor, bilinear: bool = True):
+    """Demo_WSSS.py:247-283 (discriminator_continuous=True): the UNCHANGED pair is masked with the CHANGED pair's map.
+    Returns (d_loss, cmap, ncmap, x_mask, y_mask, c_out, nc_out)."""
+    cmap = segmentor(sdS, x, y, bilinear=bilinear, train=True)
+    C = x.shape[1]
+    m = 1 - cmap.repeat(1, C, 1, 1)
+    x_mask, y_mask = x * m, y * m
+    c_out = discriminator(sdD, x_mask, y_mask, train=True)
+    ncmap = segmentor(sdS, x_nc, y_nc, bilinear=bilinear, train=True)
+    nc_out = discriminator(sdD, x_nc * m, y_nc * m, train=True)
+    return 1 + nc_out.mean() - c_out.mean(), cmap, ncmap, x_mask, y_mask, c_out, nc_out
+
+
+def wsss_s_loss(sdG: SD, sdD: SD, x: Tensor, y: Tensor, cmap: Tensor, ncmap: Tensor, x_mask: Tensor, y_mask: Tensor,
+                d_weight=1.0, l1_weight=1.6, g_weight=0.2, nc_weight=1.5, ssim_weight=0.0):
+    """Demo_WSSS.py:295-319 with perception weight 0; G runs in eval mode (Demo_WSSS.py:207)."""
+    nc_loss = (ncmap ** 2).mean()
+    c_out = discriminator(sdD, x_mask, y_mask, train=True)
+    y_fake = generator(sdG, x, train=False)
+    gen, ss = cgenerator_loss(y, y_fake, cmap)
+    g_loss = gen + ssim_weight * ss
+    l1 = cmap.abs().mean()
+    return d_weight * c_out.mean() + l1_weight * l1 + g_weight * g_loss + nc_weight * nc_loss

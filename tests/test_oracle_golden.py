@@ -139,6 +139,28 @@ def test_step_rsss():
     check_grad_summary(_grads(sdS), f["gradsS"], 2e-3, what="rsss S")
 
 
+def test_step_wsss():
+    f = load_golden("step_wsss.pt")
+    C = f["C"]
+    sdG = O.clone_sd(O.make_state_dict(O.generator_spec(C), 11), requires_grad=True)
+    sdS = O.clone_sd(O.make_state_dict(O.segmentor_spec(C, 1, True), 12), requires_grad=True)
+    sdD = O.clone_sd(O.make_state_dict(O.discriminator_spec(C), 13), requires_grad=True)
+    d_loss, cmap, ncmap, x_mask, y_mask, c_out, nc_out = O.wsss_d_loss(sdS, sdD, f["x"], f["y"], f["x_nc"], f["y_nc"])
+    assert abs(d_loss.item() - f["d_loss"]) < 5e-5
+    assert rel_err(cmap, f["cmap"]) < 5e-5 and rel_err(ncmap, f["ncmap"]) < 5e-5
+    assert rel_err(c_out, f["c_out"]) < 5e-5 and rel_err(nc_out, f["nc_out"]) < 5e-5
+    d_loss.backward(retain_graph=True)
+    check_grad_summary(_grads(sdD), f["gradsD"], 2e-3, what="wsss D")
+    for v in sdS.values():
+        if v.is_floating_point():
+            v.grad = None
+    d_w, l1_w, g_w, nc_w, ssim_w = f["weights"]
+    s_loss = O.wsss_s_loss(sdG, sdD, f["x"], f["y"], cmap, ncmap, x_mask, y_mask, d_w, l1_w, g_w, nc_w, ssim_w)
+    assert abs(s_loss.item() - f["s_loss"]) < 5e-5 * max(1.0, abs(f["s_loss"]))
+    s_loss.backward()
+    check_grad_summary(_grads(sdS), f["gradsS"], 2e-3, what="wsss S")
+
+
 def test_segmentor_gradient_conditioning():
     """Documents why END-TO-END Segmentor gradients are compared at 5e-2 on the GPU (tests/test_networks_gpu.py):
     in the fp64 oracle itself a 1e-5 relative input perturbation (the size of the CUDA path's forward error) moves

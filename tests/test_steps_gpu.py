@@ -2,7 +2,8 @@
 the UNMODIFIED reference running the same loop bodies (oracle/make_golden.py):
   * USSS joint iteration, Demo_USSS.py:305-341 (double backward with retain_graph; live SSIM gradient),
   * RSSS adversarial iteration, Demo_RSSS.py:285-331 (D update with gradients flowing into S through the soft
-    masks, D re-run, CGeneratorLoss + region losses).
+    masks, D re-run, CGeneratorLoss + region losses),
+  * WSSS adversarial iteration, Demo_WSSS.py:240-323 (changed + unchanged pair, 3 bands, nc_loss).
 Loss values within 2e-4 relative, change-density map within 1e-3, gradients: global cosine / norm ratio and
 per-tensor L2 (activation-kink tolerant, see tests/_util.check_grad_summary_l2)."""
 import pytest
@@ -86,3 +87,83 @@ def test_step_rsss():
     s_loss.backward()
     assert abs(s_loss.item() - f["s_loss"]) < 2e-4 * max(1.0, abs(f["s_loss"]))
     check_grad_summary_l2(_grads(netS), f["gradsS"], 5e-2, 0.5, what="rsss S")
+
+
+def test_step_wsss():
+    f = load_golden("step_wsss.pt")
+    C = f["C"]
+    netG, netS, netD = _nets(C)
+    netG.eval(); netS.train(); netD.train()
+    x, y, x_nc, y_nc = (f[k].to(DEV) for k in ("x", "y", "x_nc", "y_nc"))
+    d_w, l1_w, g_w, nc_w, ssim_w = f["weights"]
+    # --- Demo_WSSS.py:247-319 with the fused inline terms (soft_mask / mean / mean_abs / mean_sq)
+    cmap = netS(x, y)
+    x_mask = fb.soft_mask(x, cmap)
+    y_mask = fb.soft_mask(y, cmap)
+    c_out = netD(x_mask, y_mask)
+    ncmap = netS(x_nc, y_nc)
+    x_mask_nc = fb.soft_mask(x_nc, cmap)          # the unchanged pair is masked with the CHANGED pair's map
+    y_mask_nc = fb.soft_mask(y_nc, cmap)
+    nc_out = netD(x_mask_nc, y_mask_nc)
+    netD.zero_grad()
+    d_loss = 1 + fb.mean(nc_out) - fb.mean(c_out)
+    d_loss.backward(retain_graph=True)
+    assert abs(d_loss.item() - f["d_loss"]) < 2e-4
+    assert rel_err(c_out, f["c_out"]) < 1e-3 and rel_err(nc_out, f["nc_out"]) < 1e-3
+    assert rel_err(cmap, f["cmap"]) < 1e-3 and rel_err(ncmap, f["ncmap"]) < 1e-3
+    check_grad_summary_l2(_grads(netD), f["gradsD"], 5e-2, 0.5, what="wsss D")
+    nc_loss = fb.mean_sq(ncmap)
+    c_out2 = netD(x_mask, y_mask)
+    y_fake = netG(x)
+    gcrit = fb.CGeneratorLoss(channel=C)
+    gl, sl, _ = gcrit(y, y_fake, cmap)
+    g_loss = gl + ssim_w * sl
+    l1_loss = fb.mean_abs(cmap)
+    s_loss = d_w * fb.mean(c_out2) + l1_w * l1_loss + g_w * g_loss + nc_w * nc_loss
+    netS.zero_grad()
+    s_loss.backward()
+    assert abs(nc_loss.item() - f["nc_loss"]) <= 2e-4 * max(abs(f["nc_loss"]), 1e-3)
+    assert abs(l1_loss.item() - f["l1_loss"]) <= 2e-4 * max(abs(f["l1_loss"]), 1e-3)
+    assert abs(s_loss.item() - f["s_loss"]) < 2e-4 * max(1.0, abs(f["s_loss"]))
+    check_grad_summary_l2(_grads(netS), f["gradsS"], 5e-2, 0.5, what="wsss S")
+
+
+def test_step_drivers_match_golden_and_update_parameters():
+    """fcdgan_b200.steps.{usss,rsss,wsss}_step: same losses as the reference loop bodies on the first iteration, and with
+    optimizers attached every network the reference updates actually moves."""
+    f = load_golden("step_usss.pt")
+    C = f["C"]
+    netG, netS, _ = _nets(C)
+    netG.train(); netS.train()
+    out = fb.usss_step(netG, netS, f["x"].to(DEV), f["y"].to(DEV), fb.CNetLoss(channel=C), ssim_weight=f["ssim_w"],
+                       l1_weight=f["l1_w"])
+    for key, ref in zip(("generator_loss", "l1_loss", "ssim_loss"), f["losses"]):
+        assert abs(out[key].item() - ref) <= 2e-4 * max(abs(ref), 1e-3), key
+    check_grad_summary_l2(_grads(netG), f["gradsG"], 1e-2, 0.25, what="usss_step G")
+
+    f = load_golden("step_rsss.pt")
+    C = f["C"]
+    netG, netS, netD = _nets(C)
+    netG.eval(); netS.train(); netD.train()
+    out = fb.rsss_step(netG, netS, netD, f["x"].to(DEV), f["y"].to(DEV), f["region"].to(DEV), fb.CGeneratorLoss(channel=C))
+    assert abs(out["d_loss"].item() - f["d_loss"]) < 2e-4
+    assert abs(out["s_loss"].item() - f["s_loss"]) < 2e-4 * max(1.0, abs(f["s_loss"]))
+
+    f = load_golden("step_wsss.pt")
+    C = f["C"]
+    netG, netS, netD = _nets(C)
+    netG.eval(); netS.train(); netD.train()
+    optS = torch.optim.RMSprop(netS.parameters(), lr=5e-5)       # Demo_WSSS.py:121-122
+    optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5)
+    before = {n: [p.detach().clone() for p in net.parameters()] for n, net in (("S", netS), ("D", netD), ("G", netG))}
+    d_w, l1_w, g_w, nc_w, ssim_w = f["weights"]
+    out = fb.wsss_step(netG, netS, netD, *(f[k].to(DEV) for k in ("x", "y", "x_nc", "y_nc")), fb.CGeneratorLoss(channel=C),
+                       optS=optS, optD=optD, d_weight=d_w, l1_weight=l1_w, g_weight=g_w, nc_weight=nc_w, ssim_weight=ssim_w)
+    assert abs(out["d_loss"].item() - f["d_loss"]) < 2e-4
+    # s_loss is evaluated with the UPDATED discriminator here (optD stepped in between, as in the reference loop), so only
+    # the D-independent terms are compared with the no-step golden
+    assert abs(out["nc_loss"].item() - f["nc_loss"]) <= 2e-4 * max(abs(f["nc_loss"]), 1e-3)
+    assert abs(out["l1_loss"].item() - f["l1_loss"]) <= 2e-4 * max(abs(f["l1_loss"]), 1e-3)
+    moved = {n: any((p.detach() != q).any().item() for p, q in zip(net.parameters(), before[n]))
+             for n, net in (("S", netS), ("D", netD), ("G", netG))}
+    assert moved == {"S": True, "D": True, "G": False}, moved
