@@ -41,6 +41,11 @@ extern "C" {
 #define FCD_ENGINE_SIMT 1   /* fp32 CUDA-core implicit GEMM (any shape)         */
 #define FCD_ENGINE_TC 2     /* tcgen05 + TMA implicit GEMM                      */
 
+#define FCD_RASTER_F32 0  /* element types of a source raster (fcd_tiles_gather)  */
+#define FCD_RASTER_U16 1
+#define FCD_RASTER_I16 2
+#define FCD_RASTER_U8 3
+
 #define FCD_LOSS_L1 0     /* Loss.py:69  (CNetLoss)                            */
 #define FCD_LOSS_MSE 1    /* Loss.py:103 (CGeneratorLoss)                      */
 
@@ -245,6 +250,30 @@ int fcd_msssim_combine_fwd(const double* sums, const double* counts, const float
                            int size_average, int use_relu, float* prod, float* out, void* stream);
 int fcd_msssim_combine_bwd(const double* sums, const double* counts, const float* weights, int levels, int planes, int C,
                            int size_average, int use_relu, const float* prod, const float* gout, float* coef, void* stream);
+
+/* ---- rasters either side of the hot path ------------------------------------------------------
+ * All pointers are device pointers.  geom is int[n_tiles][6], one row per tile of the grid, computed once on the host
+ * (fcdgan_b200.raster.TileGrid = the geometry of GDALDataset.slice_assign, data_utils.py:151-176); items is int[B], the tile
+ * index of every batch slot (null = tiles 0..B-1).
+ *
+ * fcd_tiles_gather: GDALDataset.__getitem__ (data_utils.py:94-123) + NORMALIZE.forward (CommonFunc.py:208-224).
+ *   raster [C][H][W] of `dtype`; geom[t] = {read_x, read_y, read_w, read_h, write_x, write_y}; out [B][C][patch_h][patch_w]
+ *   fp32 = 0 outside the write window, float((double(v) - mean[c]) / std[c]) inside (mean/std null: no normalisation). */
+int fcd_tiles_gather(const void* raster, int dtype, int C, int H, int W, const int* geom, const int* items, int B,
+                     int patch_w, int patch_h, const double* mean, const double* stdv, float* out, void* stream);
+/* Dataset_mean / Dataset_std reductions (CommonFunc.py:436-499) over un-normalised tiles: valid pixels = fp32 band sum of x
+ * non-zero.  centre null: sums[b][0|1][c] += sum of x|y, counts[b] += #valid; centre = [meanX | meanY]: sums of squared
+ * deviations (counts may be null).  sums / counts must be zero-initialised. */
+int fcd_tiles_moments(const float* x_tiles, const float* y_tiles, int B, int C, int npix_per_tile, const double* centre,
+                      double* sums, long long* counts, void* stream);
+/* GDALDataset.GDALwriteDefault (data_utils.py:178-213): geom[t] = {pad_x, pad_y, slice_x, slice_y, slice_w, slice_h};
+ * tiles [B][1][patch_h][patch_w] -> raster [H][W]. */
+int fcd_tiles_scatter(const float* tiles, const int* geom, const int* items, int B, int patch_w, int patch_h, float* raster,
+                      int H, int W, void* stream);
+/* Demo_USSS.py:349-362 + Evaluator._generate_matrix_bymap (metrics.py:74-80), same geom as fcd_tiles_scatter:
+ * counts[i*2+j] += #{centre-crop pixels : int16(ref) == gt_map[i] && (cmap > thresh) == pre_map[j]}; counts is int64[4]. */
+int fcd_confusion_accumulate(const float* cmap, const float* ref, const int* geom, const int* items, int B, int patch_w,
+                             int patch_h, float thresh, int gt0, int gt1, int pre0, int pre1, long long* counts, void* stream);
 
 /* bring-up probe for the tcgen05 shared-memory descriptor semantics (scripts/gpu_probe.py); not on the product path */
 int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks, int b_blocks,
