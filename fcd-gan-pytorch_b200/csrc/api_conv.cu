@@ -49,6 +49,7 @@ int conv2d_taps_wgrad_tc(const void*, const void*, int, int, int, const void*, c
                          int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 extern bool g_wgrad_halo_enabled;
 extern bool g_conv_halo_enabled;
+extern bool g_conv_tma_out;
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream);
 
@@ -65,6 +66,10 @@ int fcd_set_option(const char* name, int value) {
     FCD_CHECK_ARG(name, "fcd_set_option: null name");
     if (strcmp(name, "wgrad_halo") == 0) {
         g_wgrad_halo_enabled = value != 0;
+        return FCD_OK;
+    }
+    if (strcmp(name, "conv_tma_out") == 0) {
+        g_conv_tma_out = value != 0;
         return FCD_OK;
     }
     if (strcmp(name, "conv_halo") == 0) {

@@ -324,6 +324,8 @@ struct ConvHaloParams {
     int box_dh, box_dw;      // box origin relative to the tile's first output pixel
     int off_h0, off_w0;      // in-box position of tap (0, 0)
     long long pix_tiles;     // N * tiles_h * tiles_w
+    int tma_out;             // 1: the epilogue stages 32 pixels x 16 channels per warp in shared memory and TMA-stores them
+    int tma_reduce;          //    (.add form when the addend IS the output buffer: in-place gradient accumulation)
 };
 
 // column sums over the 32 lanes of a warp: on return lane l holds sum_over_lanes v[l]  (31 shuffles; v is destroyed)
@@ -345,7 +347,7 @@ template <int BLOCK_N, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                 const ConvHaloParams hp) {
+                 const __grid_constant__ CUtensorMap map_z, const ConvHaloParams hp) {
     constexpr int PLANES = SPLIT ? 2 : 1;
     constexpr int WT_BYTES = BLOCK_N * 128;                  // one (tap, k-chunk) weight tile of one plane
     constexpr int ACC_COLS = SPLIT ? 2 * BLOCK_N : BLOCK_N;
@@ -363,6 +365,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* w_bar = tmem_empty + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint8_t* out_stage = xsm + hp.nslots * hp.slot_bytes + 1024;     // 4 epilogue warps x 2 KB (32 pixels x 16 fp32 channels)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -378,6 +381,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             tma_prefetch_desc(&map_x_lo);
             tma_prefetch_desc(&map_w_lo);
         }
+        if (hp.tma_out) tma_prefetch_desc(&map_z);
         for (int i = 0; i < hp.nslots; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -519,6 +523,72 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             const float* arow = p.addend ? p.addend + pix * p.addend_ld + nblk * BLOCK_N : nullptr;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (hp.tma_out) {
+                // ---- TMA-store epilogue: the accumulator rows of this warp are 4 image rows x 8 pixels; 16 channels at a time
+                // go through a 2 KB staging buffer (64B-swizzled rows, conflict-free 16-byte writes) and leave as ONE bulk
+                // tensor store {16 ch, 8 w, 4 h}: full 64-byte segments instead of 32 scattered 16-byte stores per instruction,
+                // out-of-image pixels clipped by the TMA unit, in-place accumulation as a reduce-add.
+                uint8_t* stage = out_stage + q * 2048;
+                const int oh0 = th * HT_H + q * 4, ow0 = tw * HT_W;
+#pragma unroll
+                for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
+                    const int c = ci * 32;
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + acc * ACC_COLS + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (SPLIT) {   // add the x_hi * w_lo half of the stacked accumulator
+                        tmem_ld_32x32(tmem_base + acc * ACC_COLS + BLOCK_N + c + (static_cast<uint32_t>(q * 32) << 16), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                    }
+                    if (ci == BLOCK_N / 32 - 1) {      // every accumulator column is in registers: hand the buffer back
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c + j);
+                    }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const int j = half * 16 + qd * 4;
+                            *reinterpret_cast<float4*>(stage + lane * 64 + ((qd ^ ((lane >> 1) & 3)) << 4)) =
+                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int c0 = nblk * BLOCK_N + c + half * 16;
+                            if (hp.tma_reduce) tma_reduce_add_4d(&map_z, stage, c0, ow0, oh0, n);
+                            else tma_store_4d(&map_z, stage, c0, ow0, oh0, n);
+                            tma_store_commit();
+                        }
+                    }
+                    if (p.stat_sum) {
+                        float sq[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            f[j] = valid ? f[j] : 0.f;
+                            sq[j] = f[j] * f[j];
+                        }
+                        st_sum[ci] += static_cast<double>(warp_colsum32(f, lane));
+                        st_sq[ci] += static_cast<double>(warp_colsum32(sq, lane));
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+                continue;
+            }
 #pragma unroll
             for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
                 const int c = ci * 32;
@@ -568,6 +638,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 acc_phase ^= 1u;
             }
         }
+        if (hp.tma_out && lane == 0) tma_store_wait_all();
         if (p.stat_sum) {
 #pragma unroll
             for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
@@ -652,12 +723,33 @@ int make_wgt_tmap(CUtensorMap* m, const void* base, int cols, int rows, int taps
     return FCD_OK;
 }
 
+// 4D NHWC fp32 output map for the TMA-store epilogue: dims {C, W, H, N}, box {16 ch, box_w, box_h, 1}, 64B swizzle.
+int make_out_tmap(CUtensorMap* m, float* base, int C, int W, int H, int N, int ld, int box_w, int box_h) {
+    auto enc = get_encode_fn();
+    if (!enc) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        return FCD_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+    cuuint32_t box[4] = {16, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(FCD_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d (C=%d W=%d H=%d N=%d ld=%d)", (int)r, C, W, H, N, ld);
+        return FCD_ERR_CUDA;
+    }
+    return FCD_OK;
+}
+
 bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
     return (stride == 1 || stride == 2) && Cin_p % 64 == 0 && Cout_p % 64 == 0 && KH >= 1 && KW >= 1 && KH <= 9 && KW <= 9;
 }
 
 
 bool g_conv_halo_enabled = true;    // fcd_set_option("conv_halo", 0) selects the per-tap kernel everywhere
+bool g_conv_tma_out = true;         // fcd_set_option("conv_tma_out", 0): per-thread stores in the halo kernel's epilogue
 
 namespace {
 constexpr int HALO_SMEM_MAX = 227 * 1024 - 1024;   // opt-in limit minus the kernel's static shared memory
@@ -665,7 +757,7 @@ constexpr int HALO_SMEM_MAX = 227 * 1024 - 1024;   // opt-in limit minus the ker
 
 template <int BLOCK_N, bool SPLIT>
 static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
-                            const ConvHaloParams& hp, int smem_bytes, cudaStream_t stream) {
+                            const CUtensorMap& mz, const ConvHaloParams& hp, int smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         FCD_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -675,7 +767,7 @@ static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, cons
     long long grid = sm_count() / hp.c.n_blocks * hp.c.n_blocks;
     if (grid < hp.c.n_blocks) grid = hp.c.n_blocks;
     if (grid > hp.pix_tiles * hp.c.n_blocks) grid = hp.pix_tiles * hp.c.n_blocks;
-    conv_halo_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mwh, mwl, hp);
+    conv_halo_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mwh, mwl, mz, hp);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -699,7 +791,7 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
         if (p.Cout_p % bn) continue;
         if (split && bn == 128) continue;                      // 2 * (2 * 128) accumulator columns would need all of TMEM
         const long long wb = 1LL * p.n_r * p.n_s * cchunks * planes * bn * 128;
-        const long long room = HALO_SMEM_MAX - 1024 - 256 - wb;
+        const long long room = HALO_SMEM_MAX - 1024 - 1024 - 4 * 2048 - wb;    // alignment slack, barriers, output staging
         if (room < 1LL * min_slots * slot) continue;
         block_n = bn; w_bytes = static_cast<int>(wb);
         nslots = static_cast<int>(room / slot);
@@ -714,7 +806,7 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
     hp->box_dh = p.dh0 + min_dh; hp->box_dw = p.dw0 + min_dw;
     hp->off_h0 = -min_dh; hp->off_w0 = -min_dw;
     *block_n_out = block_n;
-    *smem_bytes = w_bytes + nslots * slot + 1024 + 256;
+    *smem_bytes = w_bytes + nslots * slot + 1024 + 1024 + 4 * 2048;
     return true;
 }
 
@@ -758,9 +850,16 @@ static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int
             hp.c.n_blocks = p.Cout_p / hbn;
             hp.pix_tiles = 1LL * N * hp.c.tiles_h * hp.c.tiles_w;
             hp.c.total_tiles = hp.pix_tiles * hp.c.n_blocks;
-            if (hbn == 128) return launch_conv_halo<128, false>(mxh, mxl, mwh, mwl, hp, hsmem, stream);
-            return split ? launch_conv_halo<64, true>(mxh, mxl, mwh, mwl, hp, hsmem, stream)
-                         : launch_conv_halo<64, false>(mxh, mxl, mwh, mwl, hp, hsmem, stream);
+            // TMA-store epilogue: dense output pixels, 16-byte aligned rows; the addend (if any) must be the output itself
+            CUtensorMap mz = mxh;
+            hp.tma_out = g_conv_tma_out && p.out_sh == 1 && p.out_sw == 1 && p.out_oh == 0 && p.out_ow == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.z) & 15) == 0 && p.z_ld % 4 == 0 &&
+                         (p.addend == nullptr || (p.addend == p.z && p.addend_ld == p.z_ld));
+            hp.tma_reduce = hp.tma_out && p.addend != nullptr;
+            if (hp.tma_out && (rc = make_out_tmap(&mz, p.z, p.Cout_p, p.OW, p.OH, N, p.z_ld, HT_W, 4))) return rc;
+            if (hbn == 128) return launch_conv_halo<128, false>(mxh, mxl, mwh, mwl, mz, hp, hsmem, stream);
+            return split ? launch_conv_halo<64, true>(mxh, mxl, mwh, mwl, mz, hp, hsmem, stream)
+                         : launch_conv_halo<64, false>(mxh, mxl, mwh, mwl, mz, hp, hsmem, stream);
         }
     }
     const int block_n = (p.Cout_p % 128 == 0) ? 128 : 64;
