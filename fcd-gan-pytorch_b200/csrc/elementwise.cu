@@ -308,17 +308,34 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ da, int da_ld
 
 // per-channel backward coefficients + parameter gradients:
 //   training: c1 = s1/count, c2 = s2/count;  eval: c1 = c2 = 0.   dgamma (+)= s2, dbeta (+)= s1, dslope (+)= ds.
+// dbias (optional) = gradient of the bias of the convolution that produced z = sum over pixels of dz, in closed form from
+// the same sums (dz = scale * (dy - c1 - xhat * c2)  =>  sum dz = scale * (s1 - count*c1 - c2 * sum xhat)); this replaces a
+// full read of dz by the weight-gradient call.  In training mode the result is the analytic zero up to rounding, exactly
+// like the reference's autograd value.
 __global__ void bn_bwd_finalize_kernel(const double* s1, const double* s2, double count, int train, int C, int Cp,
                                        float* c1, float* c2, float* dgamma, float* dbeta, int accumulate,
-                                       const double* ds, float* dslope) {
+                                       const double* ds, float* dslope, const float* scale, const double* zsum,
+                                       const float* mean, const float* invstd, float* dbias, int dbias_accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && dslope) *dslope = (accumulate ? *dslope : 0.f) + static_cast<float>(*ds);
     if (c >= Cp) return;
-    c1[c] = (train && c < C) ? static_cast<float>(s1[c] / count) : 0.f;
-    c2[c] = (train && c < C) ? static_cast<float>(s2[c] / count) : 0.f;
+    const float k1 = (train && c < C) ? static_cast<float>(s1[c] / count) : 0.f;
+    const float k2 = (train && c < C) ? static_cast<float>(s2[c] / count) : 0.f;
+    c1[c] = k1;
+    c2[c] = k2;
     if (c < C) {
         if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(s2[c]);
         if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(s1[c]);
+        if (dbias) {
+            double v = s1[c];
+            if (scale) {
+                const double sum_xhat = (zsum && mean && invstd)
+                                            ? (zsum[c] - count * static_cast<double>(mean[c])) * static_cast<double>(invstd[c])
+                                            : 0.0;
+                v = static_cast<double>(scale[c]) * (s1[c] - count * static_cast<double>(k1) - static_cast<double>(k2) * sum_xhat);
+            }
+            dbias[c] = (dbias_accumulate ? dbias[c] : 0.f) + static_cast<float>(v);
+        }
     }
 }
 
@@ -732,10 +749,12 @@ int fcd_bn_act_bwd_reduce(const float* da, int da_ld, const float* z, int z_ld, 
 
 int fcd_bn_bwd_finalize(const double* s1, const double* s2, double count, int training, int C, int Cp, float* c1,
                         float* c2, float* dgamma, float* dbeta, int accumulate, const double* ds, float* dslope,
-                        void* stream) {
+                        const float* scale, const double* zsum, const float* mean, const float* invstd, float* dbias,
+                        int dbias_accumulate, void* stream) {
     FCD_CHECK_ARG(s1 && s2 && c1 && c2 && count > 0, "fcd_bn_bwd_finalize: bad arguments");
     bn_bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, as_stream(stream)>>>(s1, s2, count, training, C, Cp, c1, c2,
-                                                                            dgamma, dbeta, accumulate, ds, dslope);
+                                                                            dgamma, dbeta, accumulate, ds, dslope, scale,
+                                                                            zsum, mean, invstd, dbias, dbias_accumulate);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

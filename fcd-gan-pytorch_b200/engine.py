@@ -145,11 +145,13 @@ class Act:
 class Z:
     """fp32 NHWC convolution output + BatchNorm statistics."""
 
-    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz", "pack_m")
+    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz", "pack_m", "bias_param", "db_done")
 
     def __init__(self, t, N, H, W, C, Cp):
         self.t, self.N, self.H, self.W, self.C, self.Cp, self.ld = t, N, H, W, C, Cp, Cp
         self.sum = self.sqsum = None
+        self.bias_param = None   # the producing convolution's bias: bn_act's backward may deliver its gradient (db_done)
+        self.db_done = False
         self.dz: Optional[Act] = None
         self.pack_m = 0          # > 0: the producer wants its output gradient as a PackedAct with this left margin
 
@@ -411,15 +413,17 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
           tag=f"conv_fwd_{eng} {shape}", flops=flops)
     if stats and not fuse:
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
+    z.bias_param = b
 
     def backward(tape):
         dz = z.dz
         assert dz is not None, "conv backward: output gradient missing"
         gw, acc = tape.pgrad(w)
         gb = None
-        if b is not None:
+        if b is not None and not z.db_done:
             gb, accb = tape.pgrad(b)
             assert accb == acc
+        z.db_done = False
         nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
         ws = _ws(tape.device, nbytes)
         _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
@@ -470,13 +474,16 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
         st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
         z.sum, z.sqsum = st[0], st[1]
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
+    z.bias_param = b
 
     def backward(tape):
         dz = z.dz
         assert dz is not None
         gw, acc = tape.pgrad(w)
         dwp = torch.empty((Cout, 64, KH, ng), dtype=torch.float32, device=tape.device)
-        dbt = torch.empty((Cout,), dtype=torch.float32, device=tape.device) if b is not None else None
+        need_db = b is not None and not z.db_done        # else: delivered by bn_act's backward (fcd_bn_bwd_finalize)
+        z.db_done = False
+        dbt = torch.empty((Cout,), dtype=torch.float32, device=tape.device) if need_db else None
         nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(64, Cout_p, KH, ng)
         ws = _ws(tape.device, nbytes)
         _call("fcd_conv2d_taps_wgrad", xp.p_hi(), xp.p_lo(), 64, xp.H, xp.Wp, dz.p_hi(), dz.p_lo(), dz.ld, OH, OW,
@@ -484,7 +491,7 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
               tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
         g = _w_unpack4_in(dwp, C, KW)
         gw.add_(g) if acc else gw.copy_(g)
-        if b is not None:
+        if need_db:
             gb, accb = tape.pgrad(b)
             gb.add_(dbt) if accb else gb.copy_(dbt)
         z.dz = None
@@ -603,9 +610,17 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
                 assert bn is None or acc_s == acc
                 acc = acc_s
             c = vec if vec is not None else torch.empty((6, Cp), dtype=torch.float32, device=dev)
+            # the producing convolution's bias gradient (= per-channel sum of dz) comes out of the same sums in closed form
+            gb = acc_b = None
+            if z.bias_param is not None:
+                gb, acc_b = tape.pgrad(z.bias_param)
+                z.db_done = True
+            use_stats = bn is not None and training and z.sum is not None
             _call("fcd_bn_bwd_finalize", s1.data_ptr(), s2.data_ptr(), float(npix), 1 if (training and bn is not None) else 0,
                   C, Cp, c[4].data_ptr(), c[5].data_ptr(), _lib.ptr(dgam), _lib.ptr(dbet), acc,
-                  ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl))
+                  ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl),
+                  v(0), z.sum.data_ptr() if use_stats else None, v(2) if use_stats else None, v(3) if use_stats else None,
+                  _lib.ptr(gb), acc_b or 0)
         _call("fcd_bn_act_bwd_apply", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
               sp, slope_const, dz.p_hi(), dz.p_lo(), dz.ld, npix, Cp)
         z.dz = dz
