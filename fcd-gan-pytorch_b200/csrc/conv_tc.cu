@@ -505,9 +505,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const int lh = row / HT_W, lw = row - lh * HT_W;
         int acc = 0;
         uint32_t acc_phase = 0;
-        double st_sum[BLOCK_N / 32], st_sq[BLOCK_N / 32];
+        // per-lane statistics accumulators: [32-column chunk] in the per-thread-store epilogue (lane = column),
+        // [16-column half] in the TMA-store epilogue (lane % 16 = column)
+        double st_sum[BLOCK_N / 16], st_sq[BLOCK_N / 16];
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 32; ++i) st_sum[i] = st_sq[i] = 0.0;
+        for (int i = 0; i < BLOCK_N / 16; ++i) st_sum[i] = st_sq[i] = 0.0;
         const float* bias = p.bias ? p.bias + nblk * BLOCK_N : nullptr;
         for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
             long long t = tile;
@@ -553,6 +555,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c + j);
                     }
+                    if (!valid) {       // out-of-image pixels: clipped by the TMA store, and they must not enter the statistics
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                    }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
@@ -571,16 +577,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                             else tma_store_4d(&map_z, stage, c0, ow0, oh0, n);
                             tma_store_commit();
                         }
-                    }
-                    if (p.stat_sum) {
-                        float sq[32];
+                        if (p.stat_sum) {
+                            // BatchNorm statistics from the staged tile: lane -> (column lane % 16, rows of parity lane / 16);
+                            // two adjacent 64-byte rows cover all 32 banks, so every LDS is conflict-free.
+                            const int col = lane & 15, rpar = lane >> 4;
+                            const int cq = col >> 2, cw = (col & 3) << 2;
+                            float a = 0.f, b = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            f[j] = valid ? f[j] : 0.f;
-                            sq[j] = f[j] * f[j];
+                            for (int i = 0; i < 16; ++i) {
+                                const int r = 2 * i + rpar;
+                                const float v1 = *reinterpret_cast<const float*>(stage + r * 64 + ((cq ^ ((r >> 1) & 3)) << 4) + cw);
+                                a += v1;
+                                b = fmaf(v1, v1, b);
+                            }
+                            a += __shfl_xor_sync(0xffffffffu, a, 16);
+                            b += __shfl_xor_sync(0xffffffffu, b, 16);
+                            st_sum[ci * 2 + half] += static_cast<double>(a);
+                            st_sq[ci * 2 + half] += static_cast<double>(b);
                         }
-                        st_sum[ci] += static_cast<double>(warp_colsum32(f, lane));
-                        st_sq[ci] += static_cast<double>(warp_colsum32(sq, lane));
                     }
                 }
                 if (++acc == 2) {
@@ -639,7 +653,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             }
         }
         if (hp.tma_out && lane == 0) tma_store_wait_all();
-        if (p.stat_sum) {
+        if (p.stat_sum && hp.tma_out) {
+            if (lane < 16) {
+#pragma unroll
+                for (int h16 = 0; h16 < BLOCK_N / 16; ++h16) {
+                    atomicAdd(p.stat_sum + nblk * BLOCK_N + h16 * 16 + lane, st_sum[h16]);
+                    atomicAdd(p.stat_sqsum + nblk * BLOCK_N + h16 * 16 + lane, st_sq[h16]);
+                }
+            }
+        } else if (p.stat_sum) {
 #pragma unroll
             for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
                 atomicAdd(p.stat_sum + nblk * BLOCK_N + ci * 32 + lane, st_sum[ci]);
