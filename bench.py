@@ -37,6 +37,16 @@ BATCH_PER_GPU = 16
 GF_PER_PAIR = 227.3
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can dominate the step, from the
+# committed `ncu --set full` capture profiles/r01_ncu_full_conv_engines_final.txt (B = 16, 256 x 256, 64 -> 64, parity).
+NCU_TRAFFIC_BYTES = {
+    "conv_wgrad_tc 3x3s1 64->64": 541.1e6,   # profiles/r01_ncu_wgrad_halo_roundrobin.txt (537.1 MB read + 4.0 MB written)
+    "conv_fwd_tc 3x3s1 64->64": 494.2e6,
+    "conv_dgrad_tc 3x3s1 64->64": 493.9e6,
+    "fcd_bn_act_bwd_apply": 778.4e6,
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -80,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -226,22 +236,47 @@ def run_ours(args):
     ms_total = t.item()
     value = world * B * args.steps / (ms_total / 1e3)
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> losses read back, every step
+    # ---- end to end: pinned host inputs -> H2D -> step -> losses read back, every step.
+    # The inputs of step i+1 are uploaded on a copy stream while step i computes (what a DataLoader with pinned memory and a
+    # prefetch queue does); every step's H2D copy and D2H loss read-back happen inside the timed region.
     host = synth(B, 1234 + rank, pin=True)
     h2d = sum(t_.numel() * 4 for t_ in host)
     graphed = step is not eager_step
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [[torch.empty_like(t_, device=dev) for t_ in host] for _ in range(2)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    host_losses = torch.empty(2, dtype=torch.float32).pin_memory()
 
-    def from_host():
-        # graphed: H2D straight into the graph's static input buffers; eager: fresh device tensors
-        return host if graphed else [t_.to(dev, non_blocking=True) for t_ in host]
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the step that read this slot has been issued and has run
+            for d_, h_ in zip(staging[slot], host):
+                d_.copy_(h_, non_blocking=True)
+            uploaded[slot].record(copy_stream)
 
-    for _ in range(2):
-        step(*from_host())
+    def e2e_loop(n):
+        main = torch.cuda.current_stream()
+        for ev in consumed:
+            ev.record(main)
+        upload(0)
+        out_l = None
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)
+            main.wait_event(uploaded[slot])
+            gl_, dl_ = step(*staging[slot])                  # graphed: device-to-device into the graph's static inputs
+            consumed[slot].record(main)
+            host_losses.copy_(torch.stack([gl_.detach(), dl_.detach()]), non_blocking=True)
+            main.synchronize()                               # the step's result is on the host before the next step is issued
+            out_l = host_losses.clone()
+        return out_l
+
+    e2e_loop(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        gl, dl = step(*from_host())
-        losses = torch.stack([gl.detach(), dl.detach()]).cpu()
+    losses = e2e_loop(args.steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -280,7 +315,8 @@ def run_ours(args):
         tc_fl = sum(v[2] for k, v in agg.items() if "_tc " in k)
         achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": dom_tag, "achieved": round(achieved, 1), "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4),
+                "traffic": NCU_TRAFFIC_BYTES.get(dom_tag) if args.precision == "parity" else None,
                 "launches_per_step": dom_n // nprof, "avg_launch_ms": round(dom_ms / dom_n, 4),
                 "share_of_step": round(dom_ms / tot, 3), "peak_source": pk["source"] + ", sustained bf16",
                 "tc_conv_all": {"tflops": round(tc_fl / (tc_ms * 1e-3) / 1e12, 1) if tc_ms else None,

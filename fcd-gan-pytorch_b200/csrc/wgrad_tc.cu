@@ -325,15 +325,15 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     const int ks = item % ksplit; item /= ksplit;
     const int nb = item % p.n_blocks;
     const int cb = item / p.n_blocks;
-    const long long pt_per_split = (p.total_pt + ksplit - 1) / ksplit;
     const int total_taps = p.n_r * p.n_s;
     const int tap0 = tg * p.taps_per_group;
     const int ntaps = (total_taps - tap0 < p.taps_per_group) ? total_taps - tap0 : p.taps_per_group;
     const int npairs = (ntaps + 1) >> 1;
-    long long pt_begin = ks * pt_per_split;
-    long long pt_end = pt_begin + pt_per_split;
-    if (pt_end > p.total_pt) pt_end = p.total_pt;
-    if (pt_begin > pt_end) pt_begin = pt_end;
+    // Split-K is ROUND-ROBIN over the K tiles (tile = ks, ks + ksplit, ...), not a contiguous range per CTA: every tap group
+    // then sweeps the tensor in the same global order at the same rate (the split factors are proportional to the groups'
+    // UMMA counts), so the x / dz tiles one group pulls from HBM are still in L2 when the other group asks for them
+    // (ncu: 1128 MB of DRAM reads per launch with contiguous ranges = both groups streaming the operands from HBM).
+    const long long pt_begin = ks, pt_end = p.total_pt, pt_step = ksplit;
     // split precision: [dz_hi | dz_lo] is ONE N = 128 operand, so a tap pair owns 128 accumulator columns
     constexpr int PAIR_COLS = SPLIT ? 128 : 64;
     const uint32_t need_cols = npairs * PAIR_COLS;
@@ -363,7 +363,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+            for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
                 long long t = pt;
                 const int tw = static_cast<int>(t % p.tiles_w); t /= p.tiles_w;
                 const int th = static_cast<int>(t % p.tiles_h);
@@ -410,7 +410,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             uint32_t first = 1;
-            for (long long pt = pt_begin; pt < pt_end; ++pt) {
+            for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t x_hi = smem_u32(smem + stage * p.stage_bytes);
