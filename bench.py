@@ -135,8 +135,6 @@ def run_ours(args):
         t_kill = threading.Timer(args.max_seconds, lambda: os._exit(3))
         t_kill.daemon = True
         t_kill.start()
-    if world > 1 and args.graph == "on":
-        os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
     if world > 1:
         local = P.init_from_env("nccl")
     else:
@@ -149,9 +147,9 @@ def run_ours(args):
     torch.manual_seed(0)
     netG, netD = fb.Generator(C).to(dev).train(), fb.Discriminator_SRGAN_simple(C).to(dev).train()
     P.broadcast_parameters([netG, netD])
-    # world > 1 stays eager by default: capturing the NCCL all-reduces hung on this stack (torch 2.11 / NCCL 2.28.9),
-    # see DESIGN.md §7; `--graph on` forces the capture (thread-local capture mode, NCCL async error handling off).
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    # world > 1: capturing the NCCL all-reduces INSIDE a graph hung on this stack (torch 2.11 / NCCL 2.28.9), so
+    # the iteration is captured as three graphs with the collectives issued eagerly between them.
+    use_graph = args.graph in ("on", "auto")
     optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=use_graph)   # Demo_USSS.py:121
     optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=use_graph)                   # Demo_RSSS.py:157
     crit = fb.losses._MaskedRecon
@@ -184,19 +182,55 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: the same iteration cut at its two exchange points; the pieces are CUDA graphs, the all-reduces run eagerly
+    # between them (fcdgan_b200.graph.SegmentedStep)
+    def seg_g(x, y, region, cmap):
+        y_fake = netG(x)
+        gen_loss, _, _, _ = crit.apply(y, y_fake, zero_cmap, fb.losses.LOSS_L1, False)
+        optG.zero_grad(set_to_none=True)
+        gen_loss.backward()
+        sync.pack(netG)
+        return gen_loss
+
+    def seg_d(x, y, region, cmap):
+        x_mask, y_mask = fb.soft_mask(x, cmap), fb.soft_mask(y, cmap)
+        c_out = netD(x_mask, y_mask)
+        nc_out = netD(x_mask, fb.soft_mask(y, cmap, other=x, region=region))
+        d_loss = 1 + fb.mean(nc_out) - fb.mean(c_out)
+        optD.zero_grad(set_to_none=True)
+        d_loss.backward()
+        sync.pack(netD)
+        return d_loss
+
+    def seg_opt(x, y, region, cmap):
+        sync.unpack()
+        optG.step()
+        optD.step()
+
+    def exchange_d():
+        sync.launch(netD)
+        sync.wait()
+
     data = synth(B, 1234 + rank, device=dev)
     eager_step = step
     graph_note = "eager"
     if use_graph:
         try:
-            from fcdgan_b200.graph import GraphedStep
-            gstep = GraphedStep(eager_step, data, warmup=3, capture_error_mode="thread_local" if world > 1 else "global")
+            if world == 1:
+                from fcdgan_b200.graph import GraphedStep
+                gstep = GraphedStep(eager_step, data, warmup=3)
+                graph_note = "whole iteration captured in one CUDA graph (fcdgan_b200.graph.GraphedStep)"
+            else:
+                from fcdgan_b200.graph import SegmentedStep
+                gstep = SegmentedStep([seg_g, seg_d, seg_opt], [lambda: sync.launch(netG), exchange_d], data, warmup=3)
+                graph_note = ("three CUDA graphs (G pass / D pass / optimizer steps) with the two NCCL all-reduces issued eagerly "
+                              "between them (fcdgan_b200.graph.SegmentedStep)")
 
             def step(*inputs):                      # noqa: F811 — replay; inputs are copied into the static buffers
                 if inputs and inputs[0] is not data[0]:
                     gstep.copy_inputs(*inputs)
-                return gstep()
-            graph_note = "whole iteration captured in one CUDA graph (fcdgan_b200.graph.GraphedStep)"
+                out_ = gstep()
+                return (out_[0], out_[1]) if world > 1 else out_
         except Exception as e:   # capture is an optimisation, never a requirement
             step = eager_step
             graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"

@@ -49,3 +49,62 @@ class GraphedStep:
         self.graph.replay()
         E.bump_weight_epoch()      # parameters changed on the device without their version counters moving
         return self.outputs
+
+
+class SegmentedStep:
+    """An iteration captured as SEVERAL CUDA graphs with eager calls in between — the multi-GPU form: collectives stay
+    outside the graphs (capturing NCCL all-reduces inside one graph hung on this stack), everything else is
+    replayed.
+
+        step = SegmentedStep([seg_g, seg_d, seg_opt], [launch_g, launch_d_and_wait], static_inputs)
+
+    `segments[i](*static_inputs)` are captured one after the other into graphs that share one memory pool (tensors made
+    in one segment stay valid in the next); `between[i]()` runs eagerly after segment i on every call.  Replay order:
+    graph 0, between 0, graph 1, between 1, ..., graph n-1."""
+
+    def __init__(self, segments: Sequence[Callable], between: Sequence[Callable], static_inputs: Sequence[torch.Tensor],
+                 warmup: int = 3, capture_error_mode: str = "thread_local"):
+        assert len(between) == len(segments) - 1
+        self.segments, self.between = list(segments), list(between)
+        self.static_inputs = list(static_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs, self.outputs = [], []
+        n0 = E.launch_count
+        pool = None
+        for i, seg in enumerate(self.segments):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode=capture_error_mode):
+                self.outputs.append(seg(*self.static_inputs))
+            pool = g.pool()
+            self.graphs.append(g)
+            if i < len(self.between):
+                self.between[i]()           # keeps the backend's call sequence identical on every rank during set-up
+        self.launches_per_replay = E.launch_count - n0
+        torch.cuda.synchronize()
+        E.bump_weight_epoch()
+
+    def _eager(self):
+        outs = []
+        for i, seg in enumerate(self.segments):
+            outs.append(seg(*self.static_inputs))
+            if i < len(self.between):
+                self.between[i]()
+        return outs
+
+    def copy_inputs(self, *tensors: torch.Tensor) -> None:
+        for dst, src in zip(self.static_inputs, tensors):
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self):
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if i < len(self.between):
+                self.between[i]()
+        E.bump_weight_epoch()
+        return self.outputs

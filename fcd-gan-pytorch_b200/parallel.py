@@ -58,9 +58,11 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._pending: List = []
         self._buckets: Dict[int, torch.Tensor] = {}
+        self._packed: Dict[int, tuple] = {}
 
-    def start(self, module: torch.nn.Module) -> None:
-        """Launch the all-reduce of `module`'s gradients (call right after its backward)."""
+    # ---- the four phases; pack / unpack are plain device work (CUDA-graph capturable), launch / wait talk to the backend ----
+    def pack(self, module: torch.nn.Module) -> None:
+        """Gather `module`'s gradients into its flat bucket (call right after its backward)."""
         if self.world == 1:
             return
         params = [p for p in module.parameters() if p.grad is not None]
@@ -72,17 +74,39 @@ class GradSync:
             flat = torch.empty(n, dtype=torch.float32, device=params[0].grad.device)
             self._buckets[id(module)] = flat
         torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._pending.append((work, flat, params))
+        self._packed[id(module)] = (flat, params)
 
-    def finish(self) -> None:
-        """Wait for every bucket in flight and write the averaged gradients back."""
-        for work, flat, params in self._pending:
+    def launch(self, module: torch.nn.Module) -> None:
+        """Start the asynchronous all-reduce of the packed bucket of `module`."""
+        flat = self._buckets.get(id(module))      # the bucket outlives pack(): under CUDA-graph replay pack() is not re-run
+        if self.world == 1 or flat is None:
+            return
+        self._pending.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self) -> None:
+        """Make the current stream wait for every all-reduce in flight."""
+        for work in self._pending:
             work.wait()
+        self._pending.clear()
+
+    def unpack(self) -> None:
+        """Scale the reduced buckets by 1/world and write them back into `.grad`."""
+        for flat, params in self._packed.values():
             flat.mul_(1.0 / self.world)
             off = 0
             for p in params:
                 k = p.grad.numel()
                 p.grad.copy_(flat[off:off + k].view_as(p.grad))
                 off += k
-        self._pending.clear()
+        self._packed.clear()
+
+    # ---- eager composition ------------------------------------------------------------------------------------------
+    def start(self, module: torch.nn.Module) -> None:
+        """Launch the all-reduce of `module`'s gradients (call right after its backward)."""
+        self.pack(module)
+        self.launch(module)
+
+    def finish(self) -> None:
+        """Wait for every bucket in flight and write the averaged gradients back."""
+        self.wait()
+        self.unpack()

@@ -47,6 +47,16 @@ def _worker(rank, world, port, out):
     sync.start(b)
     sync.finish()
     grads = [p.grad.clone() for p in list(a.parameters()) + list(b.parameters())]
+    # the same exchange in its four phases (pack / launch / wait / unpack), the form bench.py replays from CUDA graphs at
+    # N > 1; launch() must keep working after unpack() has run (a graph replay does not re-run pack())
+    for i, p in enumerate(list(a.parameters()) + list(b.parameters())):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    sync.pack(a); sync.launch(a); sync.pack(b); sync.launch(b); sync.wait(); sync.unpack()
+    for g, p in zip(grads, list(a.parameters()) + list(b.parameters())):
+        assert torch.equal(g, p.grad)
+    sync._buckets[id(a)].fill_(float(rank))            # "replay": the bucket was refilled on the device, pack() not called
+    sync.launch(a); sync.wait()
+    assert torch.allclose(sync._buckets[id(a)], torch.full_like(sync._buckets[id(a)], float(sum(range(world)))))
     gathered = [None] * world
     dist.all_gather_object(gathered, (w_after_bcast, grads))
     if rank == 0:
