@@ -798,7 +798,7 @@ static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, cons
 // CTA's weight block resident in shared memory next to >= 3 (split) / 2 plane slots.
 static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, int* block_n_out, ConvHaloParams* hp,
                            int* smem_bytes) {
-    if (!g_conv_halo_enabled || csh != 1 || csw != 1 || p.n_r * p.n_s < 2) return false;
+    if (!g_conv_halo_enabled || csh != 1 || csw != 1 || p.n_r * p.n_s < 1) return false;
     const int span_h = (p.n_r - 1) * (p.dh_step < 0 ? -p.dh_step : p.dh_step);
     const int span_w = (p.n_s - 1) * (p.dw_step < 0 ? -p.dw_step : p.dw_step);
     const int halo_h = HT_H + span_h, halo_w = HT_W + span_w;

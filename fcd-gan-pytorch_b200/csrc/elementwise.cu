@@ -83,6 +83,38 @@ __global__ void stage_kernel(const float* __restrict__ src, const float* __restr
     }
 }
 
+// NCHW fp32 (N,C,H,W) -> split NHWC (N,OH,OW,Kp) holding, per OUTPUT pixel of a 3x3 / stride 2 / pad 1 convolution, its whole
+// receptive field: dst[n,oh,ow,(r*3+s)*C + c] = src[n,c,2*oh-1+r,2*ow-1+s] (0 outside the image, 0 for k >= 9*C).  The first
+// discriminator layer (Module.py:196, 13 -> 64 channels) then is ONE K = 128 GEMM over a quarter of the pixels instead of 9 taps
+// of a 64-channel zero-padded tensor (engine.py: conv_im2col_s2).  One thread = one (pixel, 8 consecutive k).
+__global__ void stage_im2col_s2_kernel(const float* __restrict__ src, int C, int H, int W, int OH, int OW, int Kp,
+                                       long long total, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int kg = Kp / 8;
+    const long long pix = idx / kg;
+    const int k0 = static_cast<int>(idx - pix * kg) * 8;
+    const int ow = static_cast<int>(pix % OW);
+    const long long t = pix / OW;
+    const int oh = static_cast<int>(t % OH);
+    const long long n = t / OH;
+    const long long HW = static_cast<long long>(H) * W;
+    const float* sn = src + n * C * HW;
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        float v = 0.f;
+        if (k < 9 * C) {
+            const int tap = k / C, c = k - tap * C;
+            const int ih = 2 * oh - 1 + tap / 3, iw = 2 * ow - 1 + tap % 3;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = sn[c * HW + static_cast<long long>(ih) * W + iw];
+        }
+        r.v[j] = v;
+    }
+    st_split8(hi, lo, static_cast<size_t>(pix) * Kp + k0, r);
+}
+
 // NCHW fp32 (N,C<=16,H,W) -> split NHWC (N,H,W+M,64) with FOUR horizontally adjacent pixels packed into the channel
 // axis: dst[n,h,w'',j*16+c] = src[n,c,h,w''-M+j] (0 outside).  A 9x9 convolution over 13 bands then needs
 // ceil(9/4) = 3 taps of 64 channels per filter row instead of 9 (engine.py: conv_small_in / conv_small_out).
@@ -339,39 +371,50 @@ __global__ void bn_bwd_finalize_kernel(const double* s1, const double* s2, doubl
     }
 }
 
-// dz = scale * (dy - c1 - xhat * c2), dy = da * act'(u);  written split (operand of dgrad / wgrad)
+// dz = scale * (dy - c1 - xhat * c2), dy = da * act'(u);  written split (operand of dgrad / wgrad).
+// A thread owns ONE 8-channel group and walks APPLY_PIX pixels with it, so the six per-channel vectors are loaded once per
+// thread instead of once per pixel (they were 12 of the 16 load instructions of the one-pixel form).
+constexpr int APPLY_PIX = 4;
 __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ da, int da_ld, const float* __restrict__ z, int z_ld,
                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                         const float* __restrict__ c1, const float* __restrict__ c2, int act,
                                         const float* slope_ptr, float slope_const, __nv_bfloat16* dz_hi,
-                                        __nv_bfloat16* dz_lo, int dz_ld, long long npix, int Cp) {
+                                        __nv_bfloat16* dz_lo, int dz_ld, long long npix, int Cp, long long pstride) {
     const int cg = Cp / 8;
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= npix * cg) return;
-    const long long pix = idx / cg;
-    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    const long long slot = blockIdx.x * 1LL * blockDim.x + threadIdx.x;     // (pixel slot, channel group)
+    const long long pslot = slot / cg;
+    const int c0 = static_cast<int>(slot - pslot * cg) * 8;
+    if (pslot >= pstride) return;                                           // pstride = number of pixel slots
     const float slope = slope_ptr ? *slope_ptr : slope_const;
-    const F8 dd = ld_f32x8(da + static_cast<size_t>(pix) * da_ld + c0);
-    F8 out;
+    F8 sc, sh, mu, is, k1, k2;
     if (scale) {
-        const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
-        const F8 sc = ld_f32x8(scale + c0), sh = ld_f32x8(shift + c0), mu = ld_f32x8(mean + c0),
-                 is = ld_f32x8(invstd + c0), k1 = ld_f32x8(c1 + c0), k2 = ld_f32x8(c2 + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float u = fmaf(zz.v[j], sc.v[j], sh.v[j]);
-            const float dy = dd.v[j] * act_grad(act, u, slope);
-            out.v[j] = sc.v[j] * (dy - k1.v[j] - (zz.v[j] - mu.v[j]) * is.v[j] * k2.v[j]);
-        }
-    } else if (act != FCD_ACT_NONE) {
-        const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) out.v[j] = dd.v[j] * act_grad(act, zz.v[j], slope);
-    } else {
-        out = dd;
+        sc = ld_f32x8(scale + c0); sh = ld_f32x8(shift + c0); mu = ld_f32x8(mean + c0);
+        is = ld_f32x8(invstd + c0); k1 = ld_f32x8(c1 + c0); k2 = ld_f32x8(c2 + c0);
     }
-    st_split8(dz_hi, dz_lo, static_cast<size_t>(pix) * dz_ld + c0, out);
+#pragma unroll
+    for (int it = 0; it < APPLY_PIX; ++it) {
+        const long long pix = pslot + it * pstride;
+        if (pix >= npix) break;
+        const F8 dd = ld_f32x8(da + static_cast<size_t>(pix) * da_ld + c0);
+        F8 out;
+        if (scale) {
+            const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float u = fmaf(zz.v[j], sc.v[j], sh.v[j]);
+                const float dy = dd.v[j] * act_grad(act, u, slope);
+                out.v[j] = sc.v[j] * (dy - k1.v[j] - (zz.v[j] - mu.v[j]) * is.v[j] * k2.v[j]);
+            }
+        } else if (act != FCD_ACT_NONE) {
+            const F8 zz = ld_f32x8(z + static_cast<size_t>(pix) * z_ld + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out.v[j] = dd.v[j] * act_grad(act, zz.v[j], slope);
+        } else {
+            out = dd;
+        }
+        st_split8(dz_hi, dz_lo, static_cast<size_t>(pix) * dz_ld + c0, out);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -650,6 +693,17 @@ int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, i
     return FCD_OK;
 }
 
+int fcd_stage_im2col3x3s2(const float* src, int N, int C, int H, int W, void* dst_hi, void* dst_lo, int Kp, void* stream) {
+    FCD_CHECK_ARG(src && dst_hi && N > 0 && C > 0 && H > 0 && W > 0, "fcd_stage_im2col3x3s2: bad arguments");
+    FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= 9 * C, "fcd_stage_im2col3x3s2: Kp must be a multiple of 8 and >= 9*C");
+    const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+    const long long total = 1LL * N * OH * OW * (Kp / 8);
+    stage_im2col_s2_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(src, C, H, W, OH, OW, Kp, total, BF(dst_hi),
+                                                                            BF(dst_lo));
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
 int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, int M, void* dst_hi, void* dst_lo, void* stream) {
     FCD_CHECK_ARG(src && dst_hi && C >= 1 && C <= 16 && M >= 0, "fcd_stage_nchw_to_split_pack4: needs 1 <= C <= 16");
     const long long npix = 1LL * N * H * (W + M);
@@ -766,9 +820,10 @@ int fcd_bn_act_bwd_apply(const float* da, int da_ld, const float* z, int z_ld, c
     FCD_CHECK_ARG(da && dz_hi && Cp % 8 == 0, "fcd_bn_act_bwd_apply: bad arguments");
     FCD_CHECK_ARG(!scale || (z && shift && mean && invstd && c1 && c2), "fcd_bn_act_bwd_apply: BN path needs all vectors");
     FCD_CHECK_ARG(act == FCD_ACT_NONE || z, "fcd_bn_act_bwd_apply: activation backward needs z");
-    bn_act_bwd_apply_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+    const long long pslots = (npix + APPLY_PIX - 1) / APPLY_PIX;           // pixel slots, each walks APPLY_PIX pixels
+    bn_act_bwd_apply_kernel<<<blocks_for(pslots * (Cp / 8)), NT, 0, as_stream(stream)>>>(
         da, da_ld, z, z_ld, scale, shift, mean, invstd, c1, c2, act, slope_ptr, slope_const, BF(dz_hi), BF(dz_lo), dz_ld,
-        npix, Cp);
+        npix, Cp, pslots);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

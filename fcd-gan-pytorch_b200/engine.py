@@ -28,7 +28,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
 BN_MOMENTUM = 0.1
 
-_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True}
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True}
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_*.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
@@ -43,6 +43,15 @@ def set_precision(mode: str) -> None:
 
 def get_precision() -> str:
     return "parity" if _cfg["split"] else "fast"
+
+
+def im2col_enabled() -> bool:
+    """Receptive-field-packed first discriminator layer for data inputs (conv_im2col_s2); tcgen05 engine only."""
+    return _cfg["im2col"] and _cfg["engine"] != ENGINE_SIMT
+
+
+def set_im2col(on: bool) -> None:
+    _cfg["im2col"] = bool(on)
 
 
 def set_engine(engine: int) -> None:
@@ -490,6 +499,56 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
               dwp.data_ptr(), _lib.ptr(dbt), N, 64, 64, Cout, Cout_p, KH, ng, -pad, -pad + M, 4, 0, ws.data_ptr(), nbytes,
               tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
         g = _w_unpack4_in(dwp, C, KW)
+        gw.add_(g) if acc else gw.copy_(g)
+        if need_db:
+            gb, accb = tape.pgrad(b)
+            gb.add_(dbt) if accb else gb.copy_(dbt)
+        z.dz = None
+
+    tape.push(backward)
+    return z
+
+
+def conv_im2col_s2(tape: Tape, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> Z:
+    """3x3 / stride 2 / pad 1 convolution of an NCHW DATA tensor with few channels (the first discriminator layer,
+    Module.py:196: 13 -> 64): the staging kernel writes every output pixel's 3x3xC receptive field as one K = 9C row
+    (padded to a multiple of 64), so forward and weight gradient are single 1x1 GEMMs over a quarter of the pixels
+    instead of 9 taps over a 64-channel zero-padded tensor.  No input gradient (callers use `conv` when x needs one)."""
+    Cout, C, KH, KW = w.shape
+    assert (KH, KW) == (3, 3) and x.shape[1] == C
+    N, _, H, W = x.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    K = 9 * C
+    Kp, Cout_p = pad_ch(K), pad_ch(Cout)
+    x = x.contiguous()
+    a = tape.new_act(N, OH, OW, K, Cp=Kp, name="im2col")
+    _call("fcd_stage_im2col3x3s2", x.data_ptr(), N, C, H, W, a.p_hi(), a.p_lo(), Kp)
+    wf = _derived(w, "im2col", lambda t: t.permute(0, 2, 3, 1).reshape(Cout, K, 1, 1).contiguous())
+    w_hi, w_lo = _packed(wf, Cout_p, Kp, 0, "im2col")
+    bias = None if b is None else _padded_vec(b, Cout_p)
+    zt = torch.empty((N, OH, OW, Cout_p), dtype=torch.float32, device=tape.device)
+    z = Z(zt, N, OH, OW, Cout, Cout_p)
+    flops = 2.0 * N * OH * OW * Cout * C * 9
+    shape = f"3x3s2 {C}->{Cout}"
+    _call("fcd_conv2d_fwd", a.p_hi(), a.p_lo(), a.ld, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
+          zt.data_ptr(), z.ld, N, OH, OW, Kp, Cout_p, 1, 1, 1, 0, None, None, _cfg["engine"],
+          tag=f"conv_fwd_tc_im2col {shape}", flops=flops)
+    z.bias_param = b
+
+    def backward(tape):
+        dz = z.dz
+        assert dz is not None
+        gw, acc = tape.pgrad(w)
+        need_db = b is not None and not z.db_done
+        z.db_done = False
+        dwp = torch.empty((Cout, K, 1, 1), dtype=torch.float32, device=tape.device)
+        dbt = torch.empty((Cout,), dtype=torch.float32, device=tape.device) if need_db else None
+        nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, OH, OW, Kp, Cout_p, 1, 1, 1, 0, _cfg["engine"])
+        ws = _ws(tape.device, nbytes)
+        _call("fcd_conv2d_wgrad", a.p_hi(), a.p_lo(), a.ld, dz.p_hi(), dz.p_lo(), dz.ld, dwp.data_ptr(), _lib.ptr(dbt),
+              N, OH, OW, K, Kp, Cout, Cout_p, 1, 1, 1, 0, 0, ws.data_ptr(), nbytes, _cfg["engine"],
+              tag=f"conv_wgrad_tc_im2col {shape}", flops=flops)
+        g = dwp.view(Cout, 3, 3, C).permute(0, 3, 1, 2)
         gw.add_(g) if acc else gw.copy_(g)
         if need_db:
             gb, accb = tape.pgrad(b)

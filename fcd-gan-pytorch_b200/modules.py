@@ -330,9 +330,12 @@ class Discriminator_SRGAN_simple(nn.Module):
         )
         self.sigmoid = nn.Sigmoid()
 
-    def _features(self, tape, a: E.Act, training: bool, need_in: bool) -> E.Act:
+    def _features(self, tape, a, training: bool, need_in: bool) -> E.Act:
         net = self.net
-        z = E.conv(tape, a, net[0].weight, net[0].bias, 2, 1, stats=False, x_needs_grad=need_in)
+        if isinstance(a, E.Act):
+            z = E.conv(tape, a, net[0].weight, net[0].bias, 2, 1, stats=False, x_needs_grad=need_in)
+        else:       # NCHW data tensor: receptive-field-packed first layer (no input gradient needed)
+            z = E.conv_im2col_s2(tape, a, net[0].weight, net[0].bias)
         h = E.bn_act(tape, z, None, training, E.ACT_LEAKY, slope_const=0.2)
         for ci, bi in ((2, 3), (5, 6), (8, 9)):
             z = E.conv(tape, h, net[ci].weight, net[ci].bias, 2, 1, stats=training)
@@ -347,13 +350,16 @@ class Discriminator_SRGAN_simple(nn.Module):
 
         def fn(tape, inputs, need):
             training = self.training
-            a = E.stage_input(tape, inputs[0], need[0])
-            b = E.stage_input(tape, inputs[1], need[1])
+            # an input that needs no gradient (data, or masks built from a detached map) skips the 64-channel zero-padded
+            # staging: its first layer runs on receptive-field-packed rows (engine.conv_im2col_s2)
+            packed = [E.im2col_enabled() and not need[i] and 9 * self.n_channels <= 256 for i in range(2)]
+            a = inputs[0] if packed[0] else E.stage_input(tape, inputs[0], need[0])
+            b = inputs[1] if packed[1] else E.stage_input(tape, inputs[1], need[1])
             fx = self._features(tape, a, training, need[0])
             fy = self._features(tape, b, training, need[1])
             c1, c3 = self.classifier[1], self.classifier[3]
             slot = {}
             out = E.disc_head(tape, fx, fy, c1.weight, c1.bias, c3.weight, c3.bias, slot)
-            return out, slot, [a, b]
+            return out, slot, [None if packed[0] else a, None if packed[1] else b]
 
         return E.run_net(self, fn, x, y)

@@ -93,11 +93,12 @@ class GradSync:
         """Scale the reduced buckets by 1/world and write them back into `.grad`."""
         for flat, params in self._packed.values():
             flat.mul_(1.0 / self.world)
-            off = 0
+            views, off = [], 0
             for p in params:
                 k = p.grad.numel()
-                p.grad.copy_(flat[off:off + k].view_as(p.grad))
+                views.append(flat[off:off + k].view_as(p.grad))
                 off += k
+            torch._foreach_copy_([p.grad for p in params], views)      # one multi-tensor launch instead of one per parameter
         self._packed.clear()
 
     # ---- eager composition ------------------------------------------------------------------------------------------

@@ -129,6 +129,9 @@ int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, 
  * channels.  `mask` (optional, (N,1,H,W)) applies x*(1-mask): the soft masking of Demo_RSSS.py:290-291. */
 int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, int H, int W, void* dst_hi, void* dst_lo,
                             int dst_ld, int Cp, void* stream);
+/* NCHW fp32 -> split NHWC (N, OH, OW, Kp) im2col rows of a 3x3 / stride 2 / pad 1 convolution (Module.py:196, the first
+ * discriminator layer): dst[n,oh,ow,(r*3+s)*C + c] = src[n,c,2oh-1+r,2ow-1+s], zero outside the image and for k >= 9*C. */
+int fcd_stage_im2col3x3s2(const float* src, int N, int C, int H, int W, void* dst_hi, void* dst_lo, int Kp, void* stream);
 /* fp32 NHWC (pitch src_ld) -> NCHW fp32; accumulate != 0 adds into dst. */
 int fcd_unstage_f32_to_nchw(const float* src, int src_ld, int N, int C, int H, int W, float* dst, int accumulate,
                             void* stream);

@@ -158,6 +158,33 @@ def test_data_inputs_take_the_packed_13_band_path(kind, name):
     _check_running(net, sd_ref)
 
 
+@pytest.mark.parametrize("name", ["d13.pt", "d3_odd.pt"])
+def test_discriminator_data_inputs_take_the_im2col_path(name):
+    """Inputs that need no gradient (data / masks from a detached map) run the first 3x3 stride-2 layer on receptive-field-
+    packed rows (engine.conv_im2col_s2: one K = 9C GEMM); scores, parameter gradients and running statistics must match
+    the reference all the same, in both precisions' code paths (parity checked against the golden values)."""
+    from fcdgan_b200 import engine as E
+    fb.set_precision("parity")
+    f = load_golden(name)
+    net = _load(fb.Discriminator_SRGAN_simple(f["C"]), O.discriminator_spec(f["C"]), f["seed"])
+    net.train(True)
+    E.PROFILE = []
+    try:
+        out = net(f["x"].to(DEV), f["y"].to(DEV))
+        tags = [t[1] for t in E.PROFILE]
+    finally:
+        E.PROFILE = None
+    assert sum(t.startswith("conv_fwd_tc_im2col") for t in tags) == 2, tags
+    assert rel_err(out, f["out"]) < OUT_TOL
+    (out * f["r"].to(DEV)).sum().backward()
+    _, _, grads, sd_ref = _oracle("discriminator", f)
+    _check_grads(net, grads, name, GRAD_L2_SEG)
+    _check_running(net, sd_ref)
+    with torch.no_grad():                                   # inference
+        out2 = net.eval()(f["x"].to(DEV), f["y"].to(DEV))
+    assert out2.shape == f["out"].shape and torch.isfinite(out2).all()
+
+
 def test_generator_double_backward_and_fast_mode():
     """retain_graph=True + second backward (Demo_USSS.py:327,338) accumulates 2x the gradient; 'fast' precision
     stays within bf16-class error of the reference."""
