@@ -68,18 +68,35 @@ __device__ __forceinline__ void st_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 // ---------------------------------------------------------------------------------------------
 // NCHW fp32 (N,C,H,W) -> split NHWC with Cp >= C channels (zero padded).  Optional per-pixel factor
 // (1 - mask[n,0,h,w]) fuses the soft masking x*(1-cmap) of Demo_RSSS.py:290-291.
+// Block = 32 consecutive pixels of one image x all channels, through shared memory: the NCHW reads are coalesced along the
+// pixels (lane = pixel), the NHWC writes along the channels (8 lanes x 16 bytes = one pixel's 128-byte row) — a thread
+// writing its whole pixel row by itself scatters 16-byte pieces over 32 different lines per store instruction.
+constexpr int ST_PIX = 32;
+constexpr int ST_CH = 256;      // channels per block (blockIdx.z walks wider tensors in chunks)
 __global__ void stage_kernel(const float* __restrict__ src, const float* __restrict__ mask, int C, int Cp, long long HW,
                              long long npix, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld) {
-    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const long long n = pix / HW, p = pix - n * HW;
-    const float f = mask ? 1.f - mask[pix] : 1.f;
+    extern __shared__ float st_tile[];                 // [ST_PIX][cw + 1]
+    const int cbase = blockIdx.z * ST_CH;
+    const int cw = (Cp - cbase) < ST_CH ? (Cp - cbase) : ST_CH;
+    const int pitch = cw + 1;
+    const long long n = blockIdx.y;
+    const long long p0 = blockIdx.x * 1LL * ST_PIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long p = p0 + lane;
+    const bool in = p < HW;
+    const float f = (mask && in) ? 1.f - mask[n * HW + p] : 1.f;
     const float* s = src + n * C * HW + p;
-    for (int c0 = 0; c0 < Cp; c0 += 8) {
+    for (int c = warp; c < cw; c += nwarp)
+        st_tile[lane * pitch + c] = (in && cbase + c < C) ? s[(cbase + c) * HW] * f : 0.f;
+    __syncthreads();
+    const int cg = cw / 8;
+    for (int slot = threadIdx.x; slot < ST_PIX * cg; slot += blockDim.x) {
+        const int i = slot / cg, c0 = (slot - i * cg) * 8;
+        if (p0 + i >= HW) continue;
         F8 r;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r.v[j] = (c0 + j < C) ? s[(c0 + j) * HW] * f : 0.f;
-        st_split8(hi, lo, static_cast<size_t>(pix) * ld + c0, r);
+        for (int k = 0; k < 8; ++k) r.v[k] = st_tile[i * pitch + c0 + k];
+        st_split8(hi, lo, static_cast<size_t>(n * HW + p0 + i) * ld + cbase + c0, r);
     }
 }
 
@@ -88,59 +105,76 @@ __global__ void stage_kernel(const float* __restrict__ src, const float* __restr
 // discriminator layer (Module.py:196, 13 -> 64 channels) then is ONE K = 128 GEMM over a quarter of the pixels instead of 9 taps
 // of a 64-channel zero-padded tensor (engine.py: conv_im2col_s2).  One thread = one (pixel, 8 consecutive k).
 __global__ void stage_im2col_s2_kernel(const float* __restrict__ src, int C, int H, int W, int OH, int OW, int Kp,
-                                       long long total, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int kg = Kp / 8;
-    const long long pix = idx / kg;
-    const int k0 = static_cast<int>(idx - pix * kg) * 8;
-    const int ow = static_cast<int>(pix % OW);
-    const long long t = pix / OW;
-    const int oh = static_cast<int>(t % OH);
-    const long long n = t / OH;
+                                       __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    // block = 32 consecutive output pixels of one output row: the 3 input rows x (2*32 + 1) pixels x C channels they read are
+    // staged in shared memory with coalesced loads, then every (pixel, 8 consecutive k) slot is written as one 16-byte piece
+    extern __shared__ float im_tile[];                 // [3][C][IM_W]
+    constexpr int IM_W = 2 * ST_PIX + 1;
+    const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * ST_PIX;
     const long long HW = static_cast<long long>(H) * W;
-    const float* sn = src + n * C * HW;
-    F8 r;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = k0 + j;
-        float v = 0.f;
-        if (k < 9 * C) {
-            const int tap = k / C, c = k - tap * C;
-            const int ih = 2 * oh - 1 + tap / 3, iw = 2 * ow - 1 + tap % 3;
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = sn[c * HW + static_cast<long long>(ih) * W + iw];
+    const float* sn = src + static_cast<long long>(n) * C * HW;
+    const int iw0 = 2 * ow0 - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int rc = warp; rc < 3 * C; rc += nwarp) {          // one (input row, channel) line per warp pass, lanes along the row
+        const int r = rc / C, c = rc - r * C;
+        const int ih = 2 * oh - 1 + r;
+        const bool row_in = ih >= 0 && ih < H;
+        const float* line = sn + c * HW + static_cast<long long>(row_in ? ih : 0) * W;
+        for (int x = lane; x < IM_W; x += 32) {
+            const int iw = iw0 + x;
+            im_tile[rc * IM_W + x] = (row_in && iw >= 0 && iw < W) ? __ldg(line + iw) : 0.f;
         }
-        r.v[j] = v;
     }
-    st_split8(hi, lo, static_cast<size_t>(pix) * Kp + k0, r);
+    __syncthreads();
+    const int kg = Kp / 8;
+    for (int slot = threadIdx.x; slot < ST_PIX * kg; slot += blockDim.x) {
+        const int i = slot / kg, k0 = (slot - i * kg) * 8;
+        if (ow0 + i >= OW) continue;
+        F8 r;
+        int tap = k0 / C, c = k0 - tap * C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = 0.f;
+            if (tap < 9) {
+                const int tr = tap / 3, ts = tap - tr * 3;
+                v = im_tile[(tr * C + c) * IM_W + 2 * i + ts];
+            }
+            r.v[j] = v;
+            if (++c == C) {
+                c = 0;
+                ++tap;
+            }
+        }
+        const size_t pix = (static_cast<size_t>(n) * OH + oh) * OW + ow0 + i;
+        st_split8(hi, lo, pix * Kp + k0, r);
+    }
 }
 
 // NCHW fp32 (N,C<=16,H,W) -> split NHWC (N,H,W+M,64) with FOUR horizontally adjacent pixels packed into the channel
 // axis: dst[n,h,w'',j*16+c] = src[n,c,h,w''-M+j] (0 outside).  A 9x9 convolution over 13 bands then needs
 // ceil(9/4) = 3 taps of 64 channels per filter row instead of 9 (engine.py: conv_small_in / conv_small_out).
-__global__ void stage_pack4_kernel(const float* __restrict__ src, int C, int H, int W, int M, long long npix_out,
-                                   __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const long long pix = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (pix >= npix_out) return;
+__global__ void stage_pack4_kernel(const float* __restrict__ src, int C, int H, int W, int M, __nv_bfloat16* hi,
+                                   __nv_bfloat16* lo) {
+    // block = 32 consecutive packed pixels of one row; the 35 source pixels x C channels they read go through shared memory
+    __shared__ float pk_tile[16][ST_PIX + 4];
+    const int n = blockIdx.z, h = blockIdx.y, wq0 = blockIdx.x * ST_PIX;
     const int Wp = W + M;
-    const int wq = static_cast<int>(pix % Wp);
-    const long long nh = pix / Wp;
-    const int h = static_cast<int>(nh % H);
-    const long long n = nh / H;
-    const float* s = src + n * C * static_cast<long long>(H) * W + static_cast<long long>(h) * W;
     const long long HW = static_cast<long long>(H) * W;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int w = wq - M + j;
-        const bool in = w >= 0 && w < W;
-#pragma unroll
-        for (int c0 = 0; c0 < 16; c0 += 8) {
-            F8 r;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r.v[k] = (in && c0 + k < C) ? s[(c0 + k) * HW + w] : 0.f;
-            st_split8(hi, lo, static_cast<size_t>(pix) * 64 + j * 16 + c0, r);
-        }
+    const float* s = src + static_cast<long long>(n) * C * HW + static_cast<long long>(h) * W;
+    for (int e = threadIdx.x; e < 16 * (ST_PIX + 3); e += blockDim.x) {
+        const int x = e % (ST_PIX + 3), c = e / (ST_PIX + 3);
+        const int w = wq0 - M + x;
+        pk_tile[c][x] = (c < C && w >= 0 && w < W) ? s[c * HW + w] : 0.f;
     }
+    __syncthreads();
+    const int i = threadIdx.x >> 3, g = threadIdx.x & 7;      // 256 threads = 32 pixels x 8 channel groups
+    if (wq0 + i >= Wp) return;
+    const int j = g >> 1, c0 = (g & 1) * 8;
+    F8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = pk_tile[c0 + k][i + j];
+    const size_t pix = (static_cast<size_t>(n) * H + h) * Wp + wq0 + i;
+    st_split8(hi, lo, pix * 64 + g * 8, r);
 }
 
 // fp32 NHWC (pitch ld) -> NCHW fp32 (N,C,H,W); `accumulate` adds into dst.
@@ -686,9 +720,12 @@ extern "C" {
 int fcd_stage_nchw_to_split(const float* src, const float* mask, int N, int C, int H, int W, void* dst_hi, void* dst_lo,
                             int dst_ld, int Cp, void* stream) {
     FCD_CHECK_ARG(src && dst_hi && Cp % 8 == 0 && Cp >= C && dst_ld % 8 == 0, "fcd_stage_nchw_to_split: bad arguments");
-    const long long npix = 1LL * N * H * W;
-    stage_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, mask, C, Cp, 1LL * H * W, npix, BF(dst_hi),
-                                                                  BF(dst_lo), dst_ld);
+    const long long npix = 1LL * N * H * W, HW = 1LL * H * W;
+    FCD_CHECK_ARG(N <= 65535, "fcd_stage_nchw_to_split: at most 65535 images per call");
+    const size_t smem = sizeof(float) * ST_PIX * ((Cp < ST_CH ? Cp : ST_CH) + 1);
+    stage_kernel<<<dim3(static_cast<unsigned>((HW + ST_PIX - 1) / ST_PIX), N, (Cp + ST_CH - 1) / ST_CH), NT, smem,
+                   as_stream(stream)>>>(
+        src, mask, C, Cp, HW, npix, BF(dst_hi), BF(dst_lo), dst_ld);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -697,17 +734,20 @@ int fcd_stage_im2col3x3s2(const float* src, int N, int C, int H, int W, void* ds
     FCD_CHECK_ARG(src && dst_hi && N > 0 && C > 0 && H > 0 && W > 0, "fcd_stage_im2col3x3s2: bad arguments");
     FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= 9 * C, "fcd_stage_im2col3x3s2: Kp must be a multiple of 8 and >= 9*C");
     const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-    const long long total = 1LL * N * OH * OW * (Kp / 8);
-    stage_im2col_s2_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(src, C, H, W, OH, OW, Kp, total, BF(dst_hi),
-                                                                            BF(dst_lo));
+    FCD_CHECK_ARG(N <= 65535 && OH <= 65535, "fcd_stage_im2col3x3s2: dims exceed the launch grid");
+    const size_t smem = sizeof(float) * 3 * C * (2 * ST_PIX + 1);
+    FCD_CHECK_ARG(smem <= 48 * 1024, "fcd_stage_im2col3x3s2: too many channels (%d)", C);
+    stage_im2col_s2_kernel<<<dim3((OW + ST_PIX - 1) / ST_PIX, OH, N), NT, smem, as_stream(stream)>>>(src, C, H, W, OH, OW, Kp,
+                                                                                                  BF(dst_hi), BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
 
 int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, int M, void* dst_hi, void* dst_lo, void* stream) {
     FCD_CHECK_ARG(src && dst_hi && C >= 1 && C <= 16 && M >= 0, "fcd_stage_nchw_to_split_pack4: needs 1 <= C <= 16");
-    const long long npix = 1LL * N * H * (W + M);
-    stage_pack4_kernel<<<blocks_for(npix), NT, 0, as_stream(stream)>>>(src, C, H, W, M, npix, BF(dst_hi), BF(dst_lo));
+    FCD_CHECK_ARG(N <= 65535 && H <= 65535 && M <= 4, "fcd_stage_nchw_to_split_pack4: dims exceed the launch grid / margin > 4");
+    stage_pack4_kernel<<<dim3((W + M + ST_PIX - 1) / ST_PIX, H, N), NT, 0, as_stream(stream)>>>(src, C, H, W, M, BF(dst_hi),
+                                                                                              BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
