@@ -197,14 +197,18 @@ __global__ void fc_bwd_act_kernel(const float* dout, const float* pre, const flo
     du[i] = g;
 }
 // din[n][i] = sum_o du[n][o] w[o][i]
+// (blockIdx.y splits the O loop into chunks of FC_OCHUNK so that the 16 x 512 outputs of the discriminator head keep more than
+// 32 blocks busy; partial sums meet in `din`, which the wrapper zeroes first)
+constexpr int FC_OCHUNK = 64;
 __global__ void fc_bwd_input_kernel(const float* __restrict__ du, const float* __restrict__ w, int N, int I, int O,
                                     float* __restrict__ din) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * I) return;
     const int n = idx / I, i = idx % I;
+    const int o0 = blockIdx.y * FC_OCHUNK, o1 = o0 + FC_OCHUNK < O ? o0 + FC_OCHUNK : O;
     float acc = 0.f;
-    for (int o = 0; o < O; ++o) acc = fmaf(du[n * O + o], w[static_cast<size_t>(o) * I + i], acc);
-    din[idx] = acc;
+    for (int o = o0; o < o1; ++o) acc = fmaf(du[n * O + o], w[static_cast<size_t>(o) * I + i], acc);
+    atomicAdd(din + idx, acc);
 }
 // dw[o][i] (+)= sum_n du[n][o] in[n][i];  db[o] (+)= sum_n du[n][o]
 __global__ void fc_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int N, int I, int O,
@@ -331,7 +335,10 @@ int fcd_fc_bwd(const float* dout, const float* pre, const float* out, const floa
     FCD_CHECK_ARG(dout && in && w && du && dw && db, "fcd_fc_bwd: null pointer");
     cudaStream_t s = as_stream(stream);
     fc_bwd_act_kernel<<<(N * O + NT - 1) / NT, NT, 0, s>>>(dout, pre, out, N * O, act, du);
-    if (din) fc_bwd_input_kernel<<<(N * I + NT - 1) / NT, NT, 0, s>>>(du, w, N, I, O, din);
+    if (din) {
+        FCD_CUDA_OK(cudaMemsetAsync(din, 0, sizeof(float) * N * I, s));
+        fc_bwd_input_kernel<<<dim3((N * I + NT - 1) / NT, (O + FC_OCHUNK - 1) / FC_OCHUNK), NT, 0, s>>>(du, w, N, I, O, din);
+    }
     fc_bwd_weight_kernel<<<blocks_for(1LL * O * I), NT, 0, s>>>(du, in, N, I, O, dw, db, accumulate);
     FCD_LAUNCH_OK();
     return FCD_OK;

@@ -29,7 +29,7 @@ BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,
 BN_MOMENTUM = 0.1
 
 _cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True}
-DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_*.py)
+DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_g2.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
 

@@ -18,6 +18,7 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--precision", default="parity")
 ap.add_argument("--out", default="gpurun_out")
 ap.add_argument("--which", default="usss,rsss")
+ap.add_argument("--graph", action="store_true", help="replay each step from one CUDA graph (fcdgan_b200.graph.GraphedStep)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 fb.set_precision(args.precision)
@@ -32,8 +33,8 @@ scale = (args.size / 256.0) ** 2
 
 def usss():
     netG.train(); netS.train()
-    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99))
-    optS = torch.optim.Adam(netS.parameters(), lr=2e-4, betas=(0.9, 0.99))
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=args.graph)
+    optS = torch.optim.Adam(netS.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=args.graph)
     crit = fb.CNetLoss(channel=C)
 
     def step():
@@ -53,8 +54,8 @@ def usss():
 
 def rsss():
     netG.eval(); netS.train(); netD.train()
-    optS = torch.optim.RMSprop(netS.parameters(), lr=5e-5)
-    optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5)
+    optS = torch.optim.RMSprop(netS.parameters(), lr=5e-5, capturable=args.graph)
+    optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=args.graph)
     gcrit = fb.CGeneratorLoss(channel=C)
 
     def step():
@@ -80,7 +81,16 @@ def rsss():
 
 
 for name in args.which.split(","):
-    step = {"usss": usss, "rsss": rsss}[name]()
+    step = eager = {"usss": usss, "rsss": rsss}[name]()
+    launch = "eager"
+    if args.graph:
+        try:
+            from fcdgan_b200.graph import GraphedStep
+            g = GraphedStep(lambda: eager(), [], warmup=3)
+            step = lambda: g()
+            launch = "one CUDA graph"
+        except Exception as e:
+            launch = f"eager (capture failed: {type(e).__name__}: {str(e)[:100]})"
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -91,13 +101,13 @@ for name in args.which.split(","):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     E.PROFILE = []
-    step(); torch.cuda.synchronize()
+    eager(); torch.cuda.synchronize()
     agg = {}
     for n, tag, fl, nb, a, b in E.PROFILE:
         d = agg.setdefault(tag, [0.0, 0, 0.0]); d[0] += a.elapsed_time(b); d[1] += 1; d[2] += fl
     E.PROFILE = None
     tot = sum(v[0] for v in agg.values())
-    res = {"step": name, "batch": B, "size": args.size, "precision": args.precision, "ms_per_step": round(ms, 2),
+    res = {"step": name, "batch": B, "size": args.size, "precision": args.precision, "launch": launch, "ms_per_step": round(ms, 2),
            "tile_pairs_per_s": round(B / ms * 1e3, 2), "algorithmic_tflops": round(GF[name] * scale * B / ms, 1),
            "kernel_ms_sum": round(tot, 2), "loss": float(loss), "peak_mem_GiB": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
     print(json.dumps(res), flush=True)

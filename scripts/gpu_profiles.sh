@@ -4,9 +4,9 @@ mkdir -p gpurun_out
 timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --profile-out gpurun_out/table_parity.txt 2>gpurun_out/bench_parity.err | tee gpurun_out/bench_parity.json | cut -c1-200
 timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --precision fast --no-cpu-baseline --profile-out gpurun_out/table_fast.txt 2>/dev/null | tee gpurun_out/bench_fast.json | cut -c1-200
 timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --graph off --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_parity_eager.json | cut -c1-200
-# launch list: eager mode so that every kernel of one step is visible to ncu (graph replays are one launch)
-timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-9000} --csv \
-    --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --graph off --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+# launch list of ONE eager iteration (bounded: ncu serialises and replays every profiled launch; a whole bench.py run under ncu takes > 15 min)
+timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file gpurun_out/launches.csv python scripts/ncu_step.py > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-200
 wc -l gpurun_out/launches.csv
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on \
