@@ -243,9 +243,65 @@ size_t wgrad_tc_workspace(int N, int H, int W, int Cin_p, int Cout_p, int KH, in
     return sizeof(float) * static_cast<size_t>(KH) * KW * Cin_p * Cout_p;
 }
 
+// Vectorised form: a thread owns 8 consecutive channels (16-byte loads of both planes) and strides over the pixels; the
+// 256 / (C/8) pixel lanes of a block meet in shared memory, one float atomic per (block, channel).
+__global__ void channel_sum_vec_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld,
+                                       long long npix, int C, int cg, float* out) {
+    __shared__ float red[256 * 8];
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = blockDim.x / cg;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < lanes) {
+        for (long long p = blockIdx.x * 1LL * lanes + lane; p < npix; p += 1LL * gridDim.x * lanes) {
+            const size_t off = static_cast<size_t>(p) * ld + g * 8;
+            const uint4 a = *reinterpret_cast<const uint4*>(hi + off);
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(pa[k]);
+                acc[2 * k] += f.x;
+                acc[2 * k + 1] += f.y;
+            }
+            if (lo) {
+                const uint4 b = *reinterpret_cast<const uint4*>(lo + off);
+                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(pb[k]);
+                    acc[2 * k] += f.x;
+                    acc[2 * k + 1] += f.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = (lane < lanes) ? acc[k] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < cg * 8) {
+        const int c = threadIdx.x;               // channel = group * 8 + k
+        const int gg = c >> 3, k = c & 7;
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[(l * cg + gg) * 8 + k];
+        if (c < C) atomicAdd(out + c, t);
+    }
+}
+
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream) {
     if (!accumulate) FCD_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, stream));
+    const int cg = (C + 7) / 8;
+    const bool vec = ld % 8 == 0 && cg * 8 <= ld && cg <= 32 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
+                     (!lo || (reinterpret_cast<uintptr_t>(lo) & 15) == 0);
+    if (vec) {
+        const int lanes = 256 / cg;
+        long long blocks = (npix + lanes - 1) / lanes;
+        const long long cap = 4LL * sm_count();
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        channel_sum_vec_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo,
+                                                                                  ld, npix, C, cg, out);
+        FCD_LAUNCH_OK();
+        return FCD_OK;
+    }
     int gy = static_cast<int>(npix / 2048);
     if (gy < 1) gy = 1;
     if (gy > 1024) gy = 1024;

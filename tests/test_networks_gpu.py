@@ -214,3 +214,63 @@ def test_no_grad_inference():
     with torch.no_grad():
         cmap = net(f["x"].to(DEV), f["y"].to(DEV))
     assert not cmap.requires_grad and rel_err(cmap, f["cmap"]) < OUT_TOL
+
+
+def _full_pair(B, C=13, H=256, W=256, seed=77):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g)
+    y = x + 0.3 * torch.randn(B, C, H, W, generator=g)
+    y[:, :, 60:130, 80:170] = torch.randn(B, C, 70, 90, generator=g)
+    return x, y
+
+
+def test_full_size_tile_against_the_oracle():
+    """One bi-temporal pair at BASELINE's full tile size (13 x 256 x 256): generator image, change-density map and
+    discriminator score against the CPU oracle (pinned to the unmodified reference) within the north-star tolerance."""
+    fb.set_precision("parity")
+    C = 13
+    x, y = _full_pair(1)
+    sdG, sdS, sdD = (O.make_state_dict(s, k) for s, k in ((O.generator_spec(C), 11), (O.segmentor_spec(C, 1, True), 12),
+                                                          (O.discriminator_spec(C), 13)))
+    netG = fb.Generator(C); netG.load_state_dict(sdG)
+    netS = fb.Segmentor(C, 1, True); netS.load_state_dict(sdS)
+    netD = fb.Discriminator_SRGAN_simple(C); netD.load_state_dict(sdD)
+    netG.to(DEV).train(); netS.to(DEV).train(); netD.to(DEV).train()
+    xd, yd = x.to(DEV), y.to(DEV)
+    with torch.no_grad():
+        y_fake, cmap = netG(xd), netS(xd, yd)
+        d_out = netD(fb.soft_mask(xd, cmap), fb.soft_mask(yd, cmap))
+        y_fake_o = O.generator(O.clone_sd(sdG), x, train=True)
+        cmap_o = O.segmentor(O.clone_sd(sdS), x, y, bilinear=True, train=True)
+        m = 1 - cmap_o
+        d_o = O.discriminator(O.clone_sd(sdD), x * m, y * m, train=True)
+    assert rel_err(y_fake, y_fake_o) < OUT_TOL
+    assert rel_err(cmap, cmap_o) < OUT_TOL           # the change-density map: north-star parity bar 1e-3
+    assert rel_err(d_out, d_o) < OUT_TOL
+
+
+def test_full_batch_properties():
+    """Size-independent properties at the bench configuration (batch 16 of 13 x 256 x 256): in eval mode (running
+    statistics) tiles are independent, so every image of the batch must give exactly the result it gives alone, whatever
+    persistent-CTA tile schedule the batch size selects; and the network is deterministic from call to call."""
+    fb.set_precision("parity")
+    C, B = 13, 16
+    x, _ = _full_pair(B, seed=78)
+    netG = fb.Generator(C); netG.load_state_dict(O.make_state_dict(O.generator_spec(C), 11))
+    netG.to(DEV).eval()
+    xd = x.to(DEV)
+    with torch.no_grad():
+        full = netG(xd)
+        again = netG(xd)
+        assert torch.equal(full, again)
+        for i in (0, 7, 15):
+            alone = netG(xd[i:i + 1])
+            assert torch.equal(full[i:i + 1], alone), f"image {i} depends on its batch neighbours"
+    # zero-padding semantics at full size: a change far from a pixel cannot reach it (receptive field of the Generator:
+    # 9x9 head + 11 3x3 layers + 9x9 tail = 19 pixels each way)
+    x2 = xd.clone()
+    x2[:, :, :32, :32] += 1.0
+    with torch.no_grad():
+        moved = netG(x2)
+    assert torch.equal(moved[:, :, 64:, 64:], full[:, :, 64:, 64:])
+    assert not torch.equal(moved[:, :, :32, :32], full[:, :, :32, :32])
