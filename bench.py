@@ -131,8 +131,9 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if args.max_seconds > 0:       # self-destruct: a hung collective must not hold N GPUs until an outer timeout
-        t_kill = threading.Timer(args.max_seconds, lambda: os._exit(3))
+    max_seconds = args.max_seconds if args.max_seconds > 0 else (900.0 if world > 1 else 0.0)
+    if max_seconds > 0:            # self-destruct: a hung collective must not hold N GPUs until an outer timeout
+        t_kill = threading.Timer(max_seconds, lambda: os._exit(3))
         t_kill.daemon = True
         t_kill.start()
     if world > 1:
@@ -452,7 +453,7 @@ def main():
     ap.add_argument("--precision", choices=["parity", "fast"], default="parity")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto", help="capture the iteration in a CUDA graph")
-    ap.add_argument("--max-seconds", type=float, default=0.0, help="hard-exit the process after this many seconds (0 = off)")
+    ap.add_argument("--max-seconds", type=float, default=0.0, help="hard-exit the process after this many seconds (0 = off at N = 1, 900 at N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of the instrumented pass here")
     args = ap.parse_args()
