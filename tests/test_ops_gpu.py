@@ -82,6 +82,9 @@ CONV_CASES = [
     (2, 44, 36, 64, 128, 3, 2, 1, E.ENGINE_TC),      #   (forward / wgrad) and parity-class dgrad
     (3, 27, 27, 128, 256, 3, 2, 1, E.ENGINE_TC),     #   odd sizes
     (2, 11, 9, 256, 512, 3, 2, 1, E.ENGINE_TC),
+    (2, 20, 24, 64, 128, 3, 1, 1, E.ENGINE_TC),      # halo kernel: two 64-wide weight blocks (split) / one 128-wide block (fast)
+    (1, 33, 17, 64, 256, 3, 1, 1, E.ENGINE_TC),      # halo kernel, n_blocks = 4 (split) / 2 (fast), ragged tiles
+    (2, 16, 16, 128, 64, 1, 1, 0, E.ENGINE_TC),      # 1x1 convolution (im2col first layer, convT pixel shuffles) on the halo kernel
 ]
 
 
@@ -150,6 +153,12 @@ def test_conv_fwd_wgrad_dgrad(case, fast):
                       Cin_p, Cout_p, K, K, stride, pad, engine, S())
         want = gx + addend[..., :Cin].permute(0, 3, 1, 2).double()
         assert rel(dx[..., :Cin].permute(0, 3, 1, 2), want) < 3e-5
+        if stride == 1:
+            # in-place accumulation (addend IS the output, the form engine.conv's backward uses: TMA reduce-add epilogue)
+            _lib.call("fcd_conv2d_fwd", g.p_hi(), g.p_lo(), g.ld, wdh.data_ptr(), None if fast else wdl.data_ptr(), None,
+                      dx.data_ptr(), Cin_p, dx.data_ptr(), Cin_p, N, OH, OW, Cout_p, Cin_p, K, K, 1, K - 1 - pad, None,
+                      None, engine, S())
+            assert rel(dx[..., :Cin].permute(0, 3, 1, 2), want + gx) < 3e-5
     finally:
         E.set_precision("parity")
 
