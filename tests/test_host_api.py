@@ -100,3 +100,39 @@ def test_train_eval_and_optimizer_plumbing():
     opt = torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.9, 0.99))   # Demo_USSS.py:121
     assert len(opt.param_groups[0]["params"]) == len(list(g.parameters()))
     assert float(g.block1[1].weight) == 0.25                             # nn.PReLU() default slope, Module.py:147
+
+
+def test_raster_tile_grid_matches_the_oracle_geometry():
+    """fcdgan_b200.raster.TileGrid (host side of the raster kernels) against the numpy restatement of GDALDataset's geometry
+    (data_utils.py:57-63, 151-176), which tests/test_raster_oracle.py pins to the unmodified reference."""
+    import numpy as np
+
+    from fcdgan_b200.raster import TileGrid
+    from oracle import raster_oracle as RO
+
+    for xs, ys, patch, pad in ((256, 256, (220, 220), (10, 10)), (463, 431, (220, 220), (10, 10)), (150, 131, (64, 48), (6, 4)),
+                               (100, 100, (30, 30), (10, 10)), (64, 64, (64, 64), (0, 0)), (65, 33, (32, 32), (1, 3))):
+        g, o = TileGrid(xs, ys, patch, pad), RO.tile_grid(xs, ys, patch, pad)
+        assert g.patch_count() == RO.patch_count(o) and len(g) == g.patch_count()[0] * g.patch_count()[1]
+        try:
+            gather, crop = g.gather_geom(), g.crop_geom()
+        except ValueError:
+            # a tile whose start equals the padding reads from 0 but is written at offset `pad` (the reference's `> 0` rule);
+            # when that overflows the patch the reference raises a numpy broadcast error, TileGrid a ValueError
+            assert any(RO.slice_assign(o, *RO.item_xy(o, i))[2][0] + RO.slice_assign(o, *RO.item_xy(o, i))[1][2] > patch[0] or
+                       RO.slice_assign(o, *RO.item_xy(o, i))[2][1] + RO.slice_assign(o, *RO.item_xy(o, i))[1][3] > patch[1]
+                       for i in range(len(g)))
+            continue
+        for i in range(len(g)):
+            sl, rd, wr = RO.slice_assign(o, *RO.item_xy(o, i))
+            assert g.slice_assign(*g.item_xy(i)) == (sl, rd, wr)
+            assert gather[i].tolist() == [rd[0], rd[1], rd[2], rd[3], wr[0], wr[1]]
+            assert crop[i].tolist() == [pad[0], pad[1], sl[0], sl[1], sl[2], sl[3]]
+        # the centre crops tile the raster exactly once
+        cover = np.zeros((ys, xs), dtype=np.int32)
+        for i in range(len(g)):
+            _, _, x0, y0, w, h = crop[i]
+            cover[y0:y0 + h, x0:x0 + w] += 1
+        assert (cover == 1).all()
+    with pytest.raises(ValueError):
+        TileGrid(100, 100, (20, 20), (10, 10))
