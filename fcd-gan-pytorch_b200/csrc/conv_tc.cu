@@ -326,6 +326,7 @@ struct ConvHaloParams {
     long long pix_tiles;     // N * tiles_h * tiles_w
     int tma_out;             // 1: the epilogue stages 32 pixels x 16 channels per warp in shared memory and TMA-stores them
     int tma_reduce;          //    (.add form when the addend IS the output buffer: in-place gradient accumulation)
+    int out_bufs;            // staging buffers per epilogue warp (1, 2 or 4 x 2 KB): more = fewer waits on the TMA unit's reads
 };
 
 // column sums over the 32 lanes of a warp: on return lane l holds sum_over_lanes v[l]  (31 shuffles; v is destroyed)
@@ -511,6 +512,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
 #pragma unroll
         for (int i = 0; i < BLOCK_N / 16; ++i) st_sum[i] = st_sq[i] = 0.0;
         const float* bias = p.bias ? p.bias + nblk * BLOCK_N : nullptr;
+        int obuf = 0;
         for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
             long long t = tile;
             const int tw = static_cast<int>(t % p.tiles_w);
@@ -530,7 +532,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 // go through a 2 KB staging buffer (64B-swizzled rows, conflict-free 16-byte writes) and leave as ONE bulk
                 // tensor store {16 ch, 8 w, 4 h}: full 64-byte segments instead of 32 scattered 16-byte stores per instruction,
                 // out-of-image pixels clipped by the TMA unit, in-place accumulation as a reduce-add.
-                uint8_t* stage = out_stage + q * 2048;
+                uint8_t* stage_ring = out_stage + q * hp.out_bufs * 2048;
                 const int oh0 = th * HT_H + q * 4, ow0 = tw * HT_W;
 #pragma unroll
                 for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
@@ -561,7 +563,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                     }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
+                        uint8_t* stage = stage_ring + obuf * 2048;
+                        if (++obuf == hp.out_bufs) obuf = 0;
+                        // the store that last used THIS buffer has finished reading it (out_bufs - 1 younger ones may be in flight)
+                        if (lane == 0) tma_store_wait_read_pending(hp.out_bufs - 1);
                         __syncwarp();
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
@@ -813,11 +818,11 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
         if (p.Cout_p % bn) continue;
         if (split && bn == 128) continue;                      // 2 * (2 * 128) accumulator columns would need all of TMEM
         const long long wb = 1LL * p.n_r * p.n_s * cchunks * planes * bn * 128;
-        const long long room = HALO_SMEM_MAX - 1024 - 1024 - 4 * 2048 - wb;    // alignment slack, barriers, output staging
+        const long long room = HALO_SMEM_MAX - 1024 - 1024 - 4 * 2048 - wb;    // alignment slack, barriers, minimal output staging
         if (room < 1LL * min_slots * slot) continue;
         block_n = bn; w_bytes = static_cast<int>(wb);
         nslots = static_cast<int>(room / slot);
-        if (nslots > 8) nslots = 8;
+        if (nslots > 4) nslots = 4;        // a one-tile look-ahead is all the MMA warp can use; the rest goes to the epilogue
         break;
     }
     if (!block_n) return false;
@@ -828,7 +833,10 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
     hp->box_dh = p.dh0 + min_dh; hp->box_dw = p.dw0 + min_dw;
     hp->off_h0 = -min_dh; hp->off_w0 = -min_dw;
     *block_n_out = block_n;
-    *smem_bytes = w_bytes + nslots * slot + 1024 + 1024 + 4 * 2048;
+    // whatever is left after the weights and the x ring deepens the epilogue's staging ring (4 warps x out_bufs x 2 KB)
+    const long long left = HALO_SMEM_MAX - 1024 - 1024 - w_bytes - 1LL * nslots * slot;
+    hp->out_bufs = left >= 4 * 4 * 2048 ? 4 : left >= 2 * 4 * 2048 ? 2 : 1;
+    *smem_bytes = w_bytes + nslots * slot + 1024 + 1024 + 4 * hp->out_bufs * 2048;
     return true;
 }
 

@@ -114,6 +114,12 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const vo
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed groups have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the `pending` most recent groups have finished reading (pending in {0, 1, 3}: staging rings of 1, 2, 4 buffers)
+__device__ __forceinline__ void tma_store_wait_read_pending(int pending) {
+    if (pending >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+    else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA, tcgen05)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
