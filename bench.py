@@ -123,7 +123,6 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import torch.nn as nn
 
     import fcdgan_b200 as fb
     from fcdgan_b200 import engine as E

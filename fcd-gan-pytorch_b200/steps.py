@@ -14,7 +14,7 @@ the parity tests use them).  The perception term is out of scope
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn as nn
