@@ -1,0 +1,118 @@
+"""The launch path bench.py uses at N = 1: a whole training iteration replayed from ONE CUDA graph
+(fcdgan_b200.graph.GraphedStep) must produce what the same iteration produces when issued eagerly — same losses, same
+parameters after several optimizer steps (up to the fp32 atomics of the weight-gradient reductions).  The segmented form
+used at N > 1 (graphs with eager NCCL calls in between) is exercised by the multi-GPU bench runs (profiles/README.md) and,
+for the exchange itself, by the gloo test of GradSync's pack / launch / wait / unpack phases (tests/test_parallel.py)."""
+import copy
+import re
+
+import pytest
+import torch
+
+import fcdgan_b200 as fb
+from fcdgan_b200.graph import GraphedStep
+from oracle import fcd_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+C, B, H, W = 4, 2, 48, 40
+
+
+def _setup():
+    torch.manual_seed(0)
+    netG = fb.Generator(C); netG.load_state_dict(O.make_state_dict(O.generator_spec(C), 11))
+    netD = fb.Discriminator_SRGAN_simple(C); netD.load_state_dict(O.make_state_dict(O.discriminator_spec(C), 13))
+    netG.to(DEV).train(); netD.to(DEV).train()
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.9, 0.99), capturable=True)
+    optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV)
+    y = (x.cpu() + 0.3 * torch.randn(B, C, H, W, generator=g)).to(DEV)
+    cmap = (0.2 * torch.rand(B, 1, H, W, generator=g)).to(DEV)
+    zero = torch.zeros(B, 1, H, W, device=DEV)
+    return netG, netD, optG, optD, x, y, cmap, zero
+
+
+def _segments(netG, netD, optG, optD, zero):
+    def seg_g(x, y, cmap):
+        y_fake = netG(x)
+        loss, _, _, _ = fb.losses._MaskedRecon.apply(y, y_fake, zero, fb.losses.LOSS_L1, False)
+        optG.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss
+
+    def seg_d(x, y, cmap):
+        c_out = netD(fb.soft_mask(x, cmap), fb.soft_mask(y, cmap))
+        nc_out = netD(fb.soft_mask(x, cmap), fb.soft_mask(x, cmap))
+        d_loss = 1 + fb.mean(nc_out) - fb.mean(c_out)
+        optD.zero_grad(set_to_none=True)
+        d_loss.backward()
+        return d_loss
+
+    def seg_opt(x, y, cmap):
+        optG.step()
+        optD.step()
+
+    return seg_g, seg_d, seg_opt
+
+
+# a convolution bias in front of a train-mode BatchNorm has an analytically zero gradient: what reaches Adam / RMSprop is rounding
+# noise whose SIGN decides a full lr-sized step, so these parameters legitimately differ from run to run (they do not affect any
+# output); everything else must agree
+_NOISE_GRAD = re.compile(r"block[2-6]\.conv[12]\.bias|block7\.0\.bias|net\.[258]\.bias")
+
+
+def _params(*nets):
+    return [(k, p.detach().clone()) for n in nets for k, p in n.named_parameters() if not _NOISE_GRAD.fullmatch(k)]
+
+
+def test_graph_replay_matches_eager():
+    fb.set_precision("parity")
+    steps = 3
+    # eager run
+    netG, netD, optG, optD, x, y, cmap, zero = _setup()
+    seg_g, seg_d, seg_opt = _segments(netG, netD, optG, optD, zero)
+    eager_losses = []
+    for _ in range(steps):
+        gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
+        seg_opt(x, y, cmap)
+        eager_losses.append((gl.item(), dl.item()))
+    want = _params(netG, netD)
+    # graph run from the same initial state; the warm-up iterations of the capture advance the optimizers too, so the
+    # initial state is restored after the capture
+    netG, netD, optG, optD, x, y, cmap, zero = _setup()
+    state = (copy.deepcopy(netG.state_dict()), copy.deepcopy(netD.state_dict()))
+    seg_g, seg_d, seg_opt = _segments(netG, netD, optG, optD, zero)
+    def whole(x, y, cmap):
+        gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
+        seg_opt(x, y, cmap)
+        return gl, dl
+
+    step = GraphedStep(whole, [x, y, cmap], warmup=2)
+    run = lambda: step()
+    assert step.launches_per_replay > 50
+    # restore IN PLACE (the graphs hold the parameter / optimizer-state addresses)
+    with torch.no_grad():
+        for net, sd in ((netG, state[0]), (netD, state[1])):
+            own = net.state_dict()
+            for k, v in sd.items():
+                own[k].copy_(v)
+        for opt in (optG, optD):                 # fresh optimizer state = zeros (step counters and moment estimates)
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+    for i in range(steps):
+        gl, dl = run()
+        assert abs(gl.item() - eager_losses[i][0]) <= 1e-4 * max(1.0, abs(eager_losses[i][0])), (i, gl.item(), eager_losses[i])
+        assert abs(dl.item() - eager_losses[i][1]) <= 1e-4 * max(1.0, abs(eager_losses[i][1])), (i, dl.item(), eager_losses[i])
+    # Adam's / RMSprop's first steps move every element by ~lr (10 lr for RMSprop) * sign(gradient): an element whose gradient
+    # is at the level of the weight-gradient reductions' atomic-order noise may take the other sign, so a few elements per tensor
+    # can legitimately differ by a couple of step sizes.  The loss trajectory above is the tight check; here the bulk of every
+    # large tensor must agree tightly and nothing may move further than a few optimizer steps.
+    for (k, got), (_, ref) in zip(_params(netG, netD), want):
+        diff = (got - ref).abs()
+        assert diff.max().item() <= 5e-3, f"{k}: max |diff| {diff.max().item():.3g}"
+        if ref.numel() >= 4096:
+            off = (diff > 1e-6 + 1e-4 * ref.abs()).float().mean().item()
+            assert off < 2e-2, f"{k}: {off:.2%} of the elements differ"
