@@ -10,10 +10,10 @@ no CPU fallback — constructing modules works anywhere, calling them needs a B2
 """
 __version__ = "0.1.0"
 
-from .engine import get_precision, set_precision  # noqa: F401
+from .engine import get_precision, get_streams, invalidate_weight_cache, set_precision, set_streams  # noqa: F401
 from .modules import (DoubleConv, Discriminator_SRGAN_simple, Down, Generator, OutConv, ResidualBlock,  # noqa: F401
                       Segmentor, Up)
 from .losses import (CGeneratorLoss, CNetLoss, PerceptionLoss, mean, mean_abs, mean_sq, region_loss,  # noqa: F401
                      soft_mask)
 from .ssim import MS_SSIM, SSIM, ms_ssim, ssim  # noqa: F401
-from .steps import rsss_step, usss_step, wsss_step  # noqa: F401
+from .steps import rsss_g_step, rsss_step, usss_g_step, usss_s_step, usss_step, wsss_step  # noqa: F401

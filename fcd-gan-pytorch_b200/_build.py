@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(ROOT, "build", "fcd_b200")
 LIB = os.path.join(HERE, "libfcd_b200.so")
+PROBES_LIB = os.path.join(HERE, "libfcd_b200_probes.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -68,5 +69,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_probes(verbose: bool = False) -> str:
+    """libfcd_b200_probes.so: the tcgen05 bring-up probes / UMMA issue-rate micro-benchmarks (csrc/probes/, declared in
+    include/fcd_b200_probes.h).  Not part of the product library and not built by build(); scripts/gpu_probe.py,
+    probe_halo.py and umma_bench*.py ask for it."""
+    build(verbose=verbose)
+    src = os.path.join(CSRC, "probes", "probe_tc.cu")
+    if os.path.exists(PROBES_LIB) and os.path.getmtime(PROBES_LIB) >= max(os.path.getmtime(src), _headers_mtime()):
+        return PROBES_LIB
+    cmd = [NVCC, *NVCC_FLAGS, "-shared", src, "-o", PROBES_LIB, "-L" + HERE, "-l:libfcd_b200.so",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+    return PROBES_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--probes" in sys.argv:
+        print(build_probes(verbose=True))

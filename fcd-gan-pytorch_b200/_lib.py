@@ -92,6 +92,27 @@ def call(name: str, *args):
     return rc
 
 
+_probes = None
+
+
+def call_probe(name: str, *args):
+    """Entry points of the separate bring-up library libfcd_b200_probes.so (include/fcd_b200_probes.h); built on demand."""
+    global _probes
+    if _probes is None:
+        from . import _build
+
+        load()
+        lib = ctypes.CDLL(_build.build_probes())
+        for fname, (restype, argtypes) in parse_header(os.path.join(ROOT, "include", "fcd_b200_probes.h")).items():
+            fn = getattr(lib, fname)
+            fn.argtypes, fn.restype = argtypes, restype
+        _probes = lib
+    rc = getattr(_probes, name)(*args)
+    if rc != 0:
+        raise FcdError(f"{name} -> {rc}: {load().fcd_last_error().decode(errors='replace')}")
+    return rc
+
+
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()

@@ -697,6 +697,67 @@ __global__ void add_f32_kernel(float* __restrict__ dst, int dst_ld, const float*
     st_f32x8(dst + static_cast<size_t>(pix) * dst_ld + c0, a);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// feature-space MSE of the perception loss (Loss.py:36,48,59): the VGG16 stack runs on ONE batch holding the masked
+// target images in its first half and the masked generated images in its second half, so the loss is the mean squared
+// difference of the two halves of a split NHWC feature tensor.
+// ---------------------------------------------------------------------------------------------
+__global__ void mse_halves_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld,
+                                      long long half_elems, long long npix, int Cp, double* __restrict__ acc) {
+    const int cg = Cp / 8;
+    const long long total = npix * cg, stride = 1LL * gridDim.x * blockDim.x;
+    float part = 0.f;
+    for (long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const long long pix = idx / cg;
+        const size_t off = static_cast<size_t>(pix) * ld + static_cast<int>(idx - pix * cg) * 8;
+        const F8 a = ld_split8(hi, lo, off), b = ld_split8(hi, lo, off + half_elems);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = a.v[j] - b.v[j];
+            part = fmaf(d, d, part);
+        }
+    }
+    __shared__ double red[NT / 32];
+    double w = warp_sum(static_cast<double>(part));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        w = threadIdx.x < NT / 32 ? red[threadIdx.x] : 0.0;
+        w = warp_sum(w);
+        if (threadIdx.x == 0) atomicAdd(acc, w);
+    }
+}
+
+// grad[first half] (+)= g * (a - b), grad[second half] (+)= -g * (a - b), g = *gout * scale
+__global__ void mse_halves_bwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld,
+                                      long long half_elems, long long npix, int Cp, const float* __restrict__ gout, float scale,
+                                      float* __restrict__ grad, int grad_ld, long long grad_half_elems, int accumulate) {
+    const int cg = Cp / 8;
+    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const long long pix = idx / cg;
+    const int c0 = static_cast<int>(idx - pix * cg) * 8;
+    const size_t off = static_cast<size_t>(pix) * ld + c0;
+    const F8 a = ld_split8(hi, lo, off), b = ld_split8(hi, lo, off + half_elems);
+    const float g = __ldg(gout) * scale;
+    float* ga = grad + static_cast<size_t>(pix) * grad_ld + c0;
+    float* gb = ga + grad_half_elems;
+    F8 ra, rb;
+    if (accumulate) {
+        ra = ld_f32x8(ga);
+        rb = ld_f32x8(gb);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float d = g * (a.v[j] - b.v[j]);
+        ra.v[j] = accumulate ? ra.v[j] + d : d;
+        rb.v[j] = accumulate ? rb.v[j] - d : -d;
+    }
+    st_f32x8(ga, ra);
+    st_f32x8(gb, rb);
+}
+
 inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + NT - 1) / NT); }
 
 inline int reduce_grid(long long npix, int lanes) {
@@ -922,6 +983,29 @@ int fcd_convT2x2_shuffle_bwd(const float* d_out, int dout_ld, int N, int h, int 
     FCD_CHECK_ARG(d_out && g_hi && Cp % 8 == 0, "fcd_convT2x2_shuffle_bwd: bad arguments");
     shuffle_down_kernel<<<blocks_for(4LL * N * h * w * (Cp / 8)), NT, 0, as_stream(stream)>>>(
         d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, BF(g_hi), BF(g_lo), plane_stride, g_ld);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_mse_halves_fwd(const void* f_hi, const void* f_lo, int f_ld, long long half_elems, long long npix, int Cp, double* acc,
+                       void* stream) {
+    FCD_CHECK_ARG(f_hi && acc && Cp % 8 == 0 && f_ld % 8 == 0 && half_elems % 8 == 0 && npix > 0, "fcd_mse_halves_fwd: bad arguments");
+    long long blocks = (npix * (Cp / 8) + NT - 1) / NT;
+    const long long cap = 8LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    mse_halves_fwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, as_stream(stream)>>>(CBF(f_hi), CBF(f_lo), f_ld, half_elems, npix,
+                                                                                        Cp, acc);
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_mse_halves_bwd(const void* f_hi, const void* f_lo, int f_ld, long long half_elems, long long npix, int Cp,
+                       const float* gout, float scale, float* grad, int grad_ld, long long grad_half_elems, int accumulate,
+                       void* stream) {
+    FCD_CHECK_ARG(f_hi && gout && grad && Cp % 8 == 0 && f_ld % 8 == 0 && grad_ld % 4 == 0 && half_elems % 8 == 0 &&
+                      grad_half_elems % 4 == 0, "fcd_mse_halves_bwd: bad arguments");
+    mse_halves_bwd_kernel<<<blocks_for(npix * (Cp / 8)), NT, 0, as_stream(stream)>>>(
+        CBF(f_hi), CBF(f_lo), f_ld, half_elems, npix, Cp, gout, scale, grad, grad_ld, grad_half_elems, accumulate);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

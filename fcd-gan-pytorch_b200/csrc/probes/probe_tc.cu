@@ -3,8 +3,9 @@
 // caller-chosen start-address shift / base_offset / major-ness, and writes the fp32 accumulator back,
 // so the descriptor semantics the convolution kernels rely on (row-shifted "halo" views of one staged
 // tile; MN-major operands for wgrad) are pinned by measurement rather than by reading of the ISA text.
-#include "fcd_common.cuh"
-#include "fcd_tc.cuh"
+#include "../fcd_common.cuh"
+#include "../fcd_tc.cuh"
+#include "../../../include/fcd_b200_probes.h"
 
 namespace fcd {
 using namespace tc;

@@ -28,7 +28,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
 BN_MOMENTUM = 0.1
 
-_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True}
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1}
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_g2.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
@@ -39,6 +39,20 @@ def set_precision(mode: str) -> None:
     if mode not in ("parity", "fast"):
         raise ValueError("precision must be 'parity' or 'fast'")
     _cfg["split"] = mode == "parity"
+
+
+def set_streams(n: int) -> None:
+    """Number of CUDA streams a network pass may use (1 = everything on the current stream).  With 2, independent work —
+    the two siamese branches of the Segmentor encoder / the Discriminator, and every weight gradient next to the
+    data-gradient chain of the backward pass — is forked onto a side stream and joined with events; under CUDA-graph
+    capture the forks become parallel branches of the graph."""
+    if n not in (1, 2):
+        raise ValueError("streams must be 1 or 2")
+    _cfg["streams"] = n
+
+
+def get_streams() -> int:
+    return _cfg["streams"]
 
 
 def get_precision() -> str:
@@ -209,6 +223,14 @@ def bump_weight_epoch() -> None:
     touching `Tensor._version`, so `graph.GraphedStep` calls this after each replay."""
     global _weight_epoch
     _weight_epoch += 1
+
+
+def invalidate_weight_cache() -> None:
+    """Public form of bump_weight_epoch().  The packed copies are keyed by (storage pointer, `Tensor._version`); writes
+    that go through `.data` (`p.data.clamp_(-1, 1)` — the WGAN clip commented out at Demo_RSSS.py:308-309 —, `p.data.copy_`,
+    EMA updates, `dist.broadcast(p.data)`) do NOT move the version counter, so call this after any such write.  Optimizer
+    steps, `load_state_dict`, `.to()` and in-place ops on the parameter itself are detected without it."""
+    bump_weight_epoch()
 
 
 def _capturing() -> bool:
@@ -397,8 +419,9 @@ def unstage_grad(a: Act) -> torch.Tensor:
 
 
 def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride: int, pad: int, stats: bool,
-         x_needs_grad: bool = True, wtag: str = "") -> Z:
-    """nn.Conv2d forward (Module.py:26-216) + recorded wgrad/dgrad."""
+         x_needs_grad: bool = True, wtag: str = "", frozen: bool = False) -> Z:
+    """nn.Conv2d forward (Module.py:26-216) + recorded wgrad/dgrad.  `frozen`: the weights are constants (the VGG16 of the
+    perception loss, Loss.py:25-27) — no weight / bias gradient is computed."""
     Cout, Cin, KH, KW = w.shape
     assert Cin == x.C, f"conv: weight expects {Cin} channels, activation has {x.C}"
     Cout_p, Cin_p = pad_ch(Cout), x.Cp
@@ -427,17 +450,18 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     def backward(tape):
         dz = z.dz
         assert dz is not None, "conv backward: output gradient missing"
-        gw, acc = tape.pgrad(w)
-        gb = None
-        if b is not None and not z.db_done:
-            gb, accb = tape.pgrad(b)
-            assert accb == acc
+        if not frozen:
+            gw, acc = tape.pgrad(w)
+            gb = None
+            if b is not None and not z.db_done:
+                gb, accb = tape.pgrad(b)
+                assert accb == acc
+            nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
+            ws = _ws(tape.device, nbytes)
+            _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
+                  N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
+                  tag=f"conv_wgrad_{eng} {shape}", flops=flops)
         z.db_done = False
-        nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
-        ws = _ws(tape.device, nbytes)
-        _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
-              N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
-              tag=f"conv_wgrad_{eng} {shape}", flops=flops)
         if x_needs_grad:
             g = x.grad
             addend = g.data_ptr() if x.ready else None
@@ -861,6 +885,54 @@ def disc_head(tape: Tape, fx: Act, fy: Act, w1, b1, w2, b2, grad_slot: dict) -> 
 
     tape.push(backward)
     return result
+
+
+class BatchHalf:
+    """Gradient view of images [n0, n0 + n) of a staged batch (what `unstage_grad` needs of an input activation)."""
+
+    def __init__(self, a: Act, n0: int, n: int):
+        self.a, self.n0 = a, n0
+        self.N, self.C, self.H, self.W, self.ld, self.hi = n, a.C, a.H, a.W, a.ld, a.hi
+
+    @property
+    def grad(self) -> torch.Tensor:
+        return self.a.grad[self.n0:self.n0 + self.N]
+
+
+def stage_two_inputs(tape: Tape, x: torch.Tensor, y: torch.Tensor) -> Act:
+    """Two NCHW fp32 tensors of equal shape -> ONE split NHWC activation holding x in the first half of the batch and y in the
+    second (the perception loss runs its frozen VGG16 on target and generated images in one pass)."""
+    N, C, H, W = x.shape
+    assert y.shape == x.shape
+    x, y = x.contiguous(), y.contiguous()
+    a = tape.new_act(2 * N, H, W, C, Cp=pad_ch(C), name="input2")
+    lo = a.lo
+    _call("fcd_stage_nchw_to_split", x.data_ptr(), None, N, C, H, W, a.hi[:N].data_ptr(), None if lo is None else lo[:N].data_ptr(),
+          a.ld, a.Cp)
+    _call("fcd_stage_nchw_to_split", y.data_ptr(), None, N, C, H, W, a.hi[N:].data_ptr(), None if lo is None else lo[N:].data_ptr(),
+          a.ld, a.Cp)
+    return a
+
+
+def mse_halves(tape: Tape, f: Act, weight: float, acc: torch.Tensor, grad_slot: dict) -> float:
+    """nn.MSELoss between the two batch halves of a feature tensor (Loss.py:36,48,59): `acc` (double[1], zero-initialised)
+    receives the sum of squared differences; returns the factor weight / numel that turns it into the weighted mean.
+    Backward adds gout * 2 * weight / numel * (a - b) to the first half's gradient and its negative to the second's."""
+    assert f.N % 2 == 0 and f.parent is None
+    npix = (f.N // 2) * f.H * f.W
+    half = npix * f.ld
+    coef = weight / float(npix * f.C)
+    _call("fcd_mse_halves_fwd", f.p_hi(), f.p_lo(), f.ld, half, npix, f.Cp, acc.data_ptr())
+
+    def backward(tape):
+        gout = grad_slot["dout"].contiguous()
+        g = f.grad
+        _call("fcd_mse_halves_bwd", f.p_hi(), f.p_lo(), f.ld, half, npix, f.Cp, gout.data_ptr(), 2.0 * coef, g.data_ptr(), f.ld,
+              half, 1 if f.ready else 0)
+        f.mark_ready()
+
+    tape.push(backward)
+    return coef
 
 
 def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:

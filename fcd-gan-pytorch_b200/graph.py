@@ -108,3 +108,72 @@ class SegmentedStep:
                 self.between[i]()
         E.bump_weight_epoch()
         return self.outputs
+
+
+class YieldingStep:
+    """The multi-GPU launch path for the step bodies of steps.py: `genfn(*static_inputs)` is a generator that yields
+    `(network, wait)` at its exchange points (steps.usss_gen / rsss_gen / wsss_gen ...).  The iteration is captured as one
+    CUDA graph per stretch between exchange points (sharing one memory pool); at each point the gradient bucket of
+    `network` is all-reduced by an eager NCCL call (`sync.launch`), and when `wait` is set the stream waits for every bucket
+    in flight and the next graph starts by writing the averaged gradients back (`sync.unpack`).  Buckets launched with
+    `wait=False` stay in flight while the following graph runs.
+
+        step = YieldingStep(lambda x, y: steps.usss_gen(netG, netS, x, y, crit, optG, optS), sync, [x, y])
+        out = step()                       # replay
+    """
+
+    def __init__(self, genfn: Callable, sync, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
+                 capture_error_mode: str = "thread_local"):
+        from .steps import drive
+
+        self.sync = sync
+        self.static_inputs = list(static_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                drive(genfn(*self.static_inputs), sync.on_grads)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs, self.actions = [], []
+        n0 = E.launch_count
+        gen = genfn(*self.static_inputs)
+        pool, unpack_next, done = None, False, False
+        while not done:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode=capture_error_mode):
+                if unpack_next:
+                    sync.unpack()
+                    unpack_next = False
+                try:
+                    net, wait = next(gen)
+                    sync.pack(net)
+                except StopIteration as e:
+                    self.outputs = e.value
+                    done = True
+            pool = g.pool()
+            self.graphs.append(g)
+            if not done:                    # keeps the backend's call sequence identical on every rank during set-up
+                sync.launch(net)
+                if wait:
+                    sync.wait()
+                    unpack_next = True
+                self.actions.append((net, wait))
+        self.launches_per_replay = E.launch_count - n0
+        torch.cuda.synchronize()
+        E.bump_weight_epoch()
+
+    def copy_inputs(self, *tensors: torch.Tensor) -> None:
+        for dst, src in zip(self.static_inputs, tensors):
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self):
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if i < len(self.actions):
+                net, wait = self.actions[i]
+                self.sync.launch(net)
+                if wait:
+                    self.sync.wait()
+        E.bump_weight_epoch()
+        return self.outputs

@@ -13,13 +13,11 @@ The reference loops over the batch in Python with a host sync per sample (Loss.p
 materialises `cmap.repeat(...)`; here one kernel reads (target, generate, cmap) once and produces the per-sample
 sums, mean|cmap| and the masked images for MS-SSIM, and one backward kernel produces every gradient.
 
-PerceptionLoss (VGG16, Loss.py:17-61) is OUT OF SCOPE for the CUDA path (its ImageNet weights
-cannot be downloaded here and it is not in the north star): it is a plain-PyTorch passthrough used only when
-weights are available; otherwise the perception term is a constant 0 and a warning is issued once.
+PerceptionLoss (VGG16, Loss.py:17-61) runs its frozen feature stack on the same conv engine as the
+networks when the caller supplies the VGG16 weights (`vgg_features=`); it never downloads anything.
 """
 from __future__ import annotations
 
-import warnings
 from typing import Optional
 
 import torch
@@ -137,7 +135,8 @@ class _Mean(torch.autograd.Function):
 
 
 class _SoftMask(torch.autograd.Function):
-    """out = (a*(1-region) + b*region) * (1 - mask); gradient flows to `mask` only (a, b, region are data)."""
+    """out = (a*(1-region) + b*region) * (1 - mask); gradient flows to `mask` and, in the plain form (no b / region), to
+    the image `a` (the perception loss masks the GENERATED image, Loss.py:43,54); b and region are data."""
 
     @staticmethod
     def forward(ctx, mask, a, b, region):
@@ -151,19 +150,24 @@ class _SoftMask(torch.autograd.Function):
             b, region = b.contiguous(), region.contiguous()
         out = torch.empty_like(a)
         _call("fcd_mask_fwd", a.data_ptr(), _lib.ptr(b), _lib.ptr(region), mask.data_ptr(), N, C, H, W, out.data_ptr())
-        ctx.state = (a, b, region)
+        ctx.state = (a, b, region, mask)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        a, b, region = ctx.state
-        if any(ctx.needs_input_grad[1:]):
-            raise NotImplementedError("soft_mask: only the mask (change-density map) receives a gradient")
+        a, b, region, mask = ctx.state
+        if any(ctx.needs_input_grad[2:]) or (ctx.needs_input_grad[1] and b is not None):
+            raise NotImplementedError("soft_mask: gradients flow to the mask and (plain form only) to the image")
         N, C, H, W = a.shape
         gout = gout.contiguous()
-        dm = torch.empty((N, 1, H, W), dtype=torch.float32, device=a.device)
-        _call("fcd_mask_bwd", gout.data_ptr(), a.data_ptr(), _lib.ptr(b), _lib.ptr(region), N, C, H, W, dm.data_ptr(), 0)
-        return dm, None, None, None
+        dm = da = None
+        if ctx.needs_input_grad[0]:
+            dm = torch.empty((N, 1, H, W), dtype=torch.float32, device=a.device)
+            _call("fcd_mask_bwd", gout.data_ptr(), a.data_ptr(), _lib.ptr(b), _lib.ptr(region), N, C, H, W, dm.data_ptr(), 0)
+        if ctx.needs_input_grad[1]:          # d(a * (1 - mask)) / da = (1 - mask): the same kernel applied to the gradient
+            da = torch.empty_like(a)
+            _call("fcd_mask_fwd", gout.data_ptr(), None, None, mask.data_ptr(), N, C, H, W, da.data_ptr())
+        return dm, da, None, None
 
 
 # ---- fused forms of the inline terms of the training loops --------------------------------------------
@@ -204,58 +208,108 @@ def region_loss(cmap, region, criterion):
     return _RegionLoss.apply(cmap, region, kind)
 
 
-# ---- perception loss: torch passthrough (out of scope for the CUDA path) ------------------------------
+# ---- perception loss: frozen VGG16 feature stack on the conv engine ------------------------------------
 class PerceptionLoss(nn.Module):
-    """Loss.py:17-61 restated over torchvision's VGG16 in plain PyTorch.  `vgg_features` lets the caller supply the
-    `vgg16().features` module (e.g. loaded from a local vgg16-397923af.pth); without it the pretrained weights are
-    requested like the reference does, and if that fails (no network) the term is disabled."""
+    """Loss.py:17-61 on the tcgen05 conv engine.
+
+    The reference builds `vgg16(pretrained=True).features.eval()` itself (Loss.py:25), i.e. it DOWNLOADS the ImageNet weights;
+    a library on a production box must not, so here the caller supplies them: `vgg_features` is torchvision's
+    `vgg16().features` module (any weights), or the path of a torchvision VGG16 state_dict (`vgg16-397923af.pth`).  Without it
+    the term is DISABLED: `forward` returns 0 and the step bodies refuse a non-zero perception weight (steps._check_perception)
+    — nothing is downloaded, nothing falls back to torch.
+
+    What runs: features[0..29] = thirteen 3x3 convolutions (+bias) + ReLU and four 2x2 max-pools, with the weights frozen
+    (Loss.py:26-27) — `engine.conv(frozen=True)` (forward + data gradient only), `engine.bn_act` without BatchNorm,
+    `engine.maxpool2` — on ONE batch that holds the masked target images in its first half and the masked generated images
+    in its second; `engine.mse_halves` is the nn.MSELoss at the selected layers (Loss.py:31-36).  `perception_perBand=True`
+    (Loss.py:50-60) feeds every band as a 3-channel grey image: all bands of all samples are batched into one pass (B*C
+    images; the per-band means divided by n_channels are the mean over that batch), and the three identical input channels
+    are folded into the first layer's weights (sum over its input-channel axis).  Gradients reach `generate_image` and, when
+    it requires one, the soft mask `cmask` — through both halves, like the reference's autograd."""
 
     FEATURE_LAYERS = [29, 22, 15, 8, 3]
 
-    def __init__(self, feature_layer=1, perception_perBand=False, vgg_features: Optional[nn.Module] = None):
+    def __init__(self, feature_layer=1, perception_perBand=False, vgg_features=None):
         super().__init__()
-        self.enabled = True
-        if vgg_features is None:
-            try:
-                from torchvision.models.vgg import vgg16
-                vgg_features = vgg16(pretrained=True).features
-            except Exception as e:  # no network / no cached weights
-                warnings.warn(f"PerceptionLoss disabled (VGG16 weights unavailable: {type(e).__name__}); the perception "
-                              "term is 0.  Pass vgg_features= to enable it.")
-                self.enabled = False
+        if isinstance(vgg_features, (str, bytes)) or hasattr(vgg_features, "__fspath__"):
+            from torchvision.models.vgg import vgg16
+
+            full = vgg16(weights=None)
+            full.load_state_dict(torch.load(vgg_features, map_location="cpu"))
+            vgg_features = full.features
+        self.enabled = vgg_features is not None
         if self.enabled:
             self.net = vgg_features.eval()
             for p in self.net.parameters():
                 p.requires_grad = False
+            for i in range(30):
+                m = self.net[i]
+                ok = ((isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3) and m.padding == (1, 1) and m.stride == (1, 1))
+                      or isinstance(m, nn.ReLU) or (isinstance(m, nn.MaxPool2d) and m.kernel_size in (2, (2, 2))))
+                if not ok:
+                    raise ValueError(f"PerceptionLoss: vgg_features[{i}] = {m} is not a VGG16 feature layer")
         feature_layer = feature_layer if feature_layer > 0 else 1
         feature_layer = feature_layer if feature_layer < 6 else 5
         self.feature_layer_list = self.FEATURE_LAYERS[:feature_layer]
         self.perception_perBand = perception_perBand
-        self.loss = nn.MSELoss()
 
-    def _features_loss(self, x, y, scale):
-        total = 0
-        for i, layer in enumerate(self.net):
-            x, y = layer(x), layer(y)
-            if i in self.feature_layer_list:
-                total = total + self.loss(x, y) / scale
-        return total
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if self.enabled:
+            self.net.eval()          # Loss.py:25: the VGG stays in eval mode whatever the criterion's mode
+        return self
+
+    def _run(self, x: torch.Tensor, y: torch.Tensor, fold_input: bool) -> torch.Tensor:
+        from . import engine as E
+
+        layers = self.feature_layer_list
+        last = max(layers)
+
+        def fn(tape, inputs, need):
+            a = E.stage_two_inputs(tape, inputs[0], inputs[1])
+            slot = {}
+            acc = torch.zeros(len(layers), dtype=torch.float64, device=tape.device)
+            coefs = []
+            h = a
+            for i in range(last + 1):
+                m = self.net[i]
+                if isinstance(m, nn.Conv2d):
+                    w = m.weight
+                    if i == 0 and fold_input:      # three identical input channels == one channel with the summed filter
+                        w = E._derived(w, "fold_in", lambda t: t.sum(1, keepdim=True).contiguous())
+                    z = E.conv(tape, h, w, m.bias, 1, 1, stats=False, x_needs_grad=(i > 0 or need[0] or need[1]), frozen=True,
+                               wtag="vgg")
+                elif isinstance(m, nn.ReLU):
+                    h = E.bn_act(tape, z, None, False, E.ACT_RELU)
+                    if i in layers:
+                        coefs.append(E.mse_halves(tape, h, 1.0 / len(layers), acc[len(coefs):], slot))
+                else:
+                    h = E.maxpool2(tape, h)
+            out = acc[0] * coefs[0]          # scalar glue: weighted means of the per-layer sums
+            for k in range(1, len(coefs)):
+                out = out + acc[k] * coefs[k]
+            out = out.to(torch.float32)
+            n = inputs[0].shape[0]
+            return out, slot, [E.BatchHalf(a, 0, n), E.BatchHalf(a, n, n)]
+
+        return E.run_net(self, fn, x, y)
 
     def forward(self, target_image, generate_image, cmask):
         if not self.enabled:
             return torch.zeros((), dtype=torch.float32, device=target_image.device)
-        layer_num = len(self.feature_layer_list)
+        for t in (target_image, generate_image, cmask):
+            _check(t, "PerceptionLoss")
+        B, C, H, W = target_image.shape
+        if min(H, W) < 16:
+            raise ValueError("PerceptionLoss: images must be at least 16x16 (four 2x2 poolings)")
         if not self.perception_perBand:
-            assert target_image.shape[1] >= 3
-            m = 1 - cmask
-            return self._features_loss(target_image[:, 0:3] * m, generate_image[:, 0:3] * m, layer_num)
-        n_channels = target_image.shape[1]
-        total = 0
-        for b in range(n_channels):
-            x = (target_image[:, b:b + 1] * (1 - cmask)).repeat((1, 3, 1, 1))
-            y = (generate_image[:, b:b + 1] * (1 - cmask)).repeat((1, 3, 1, 1))
-            total = total + self._features_loss(x, y, layer_num * n_channels)
-        return total
+            assert C >= 3
+            x = soft_mask(target_image[:, 0:3].contiguous(), cmask)
+            y = soft_mask(generate_image[:, 0:3].contiguous(), cmask)
+            return self._run(x, y, False)
+        x = soft_mask(target_image, cmask).reshape(B * C, 1, H, W)
+        y = soft_mask(generate_image, cmask).reshape(B * C, 1, H, W)
+        return self._run(x, y, True)
 
 
 class CNetLoss(nn.Module):
@@ -270,7 +324,7 @@ class CNetLoss(nn.Module):
     def forward(self, target_image, generate_image, cmap, generator_mask_switch=False):
         generator_loss, l1_loss, tm, gm = _MaskedRecon.apply(target_image, generate_image, cmap, LOSS_L1, True)
         if self.loss_perception.enabled:
-            cmask = (torch.sign(cmap - 0.5) + 1) / 2 if generator_mask_switch else cmap
+            cmask = ((torch.sign(cmap.detach() - 0.5) + 1) / 2) if generator_mask_switch else cmap     # Loss.py:75,89-92
             perception_loss = self.loss_perception(target_image, generate_image, cmask)
         else:
             perception_loss = self.loss_perception(target_image, generate_image, cmap)

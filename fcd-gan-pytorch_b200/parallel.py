@@ -48,6 +48,11 @@ def broadcast_parameters(modules: Iterable[torch.nn.Module], src: int = 0, group
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+    # the broadcast wrote through `.data`: version counters did not move, so packed conv weights made by an earlier forward
+    # would be stale (engine._packed)
+    from . import engine
+
+    engine.invalidate_weight_cache()
 
 
 class GradSync:
@@ -111,3 +116,10 @@ class GradSync:
         """Wait for every bucket in flight and write the averaged gradients back."""
         self.wait()
         self.unpack()
+
+    def on_grads(self, module: torch.nn.Module, wait: bool) -> None:
+        """Exchange-point callback of the step bodies (steps.py): `module`'s gradients are complete; `wait` = the next
+        statement is an optimizer step that needs every bucket in flight."""
+        self.start(module)
+        if wait:
+            self.finish()

@@ -258,6 +258,18 @@ int fcd_msssim_combine_fwd(const double* sums, const double* counts, const float
 int fcd_msssim_combine_bwd(const double* sums, const double* counts, const float* weights, int levels, int planes, int C,
                            int size_average, int use_relu, const float* prod, const float* gout, float* coef, void* stream);
 
+/* Feature-space MSE of PerceptionLoss (Loss.py:36,48,59).  The VGG16 feature stack (Loss.py:25, torchvision vgg16.features[0..29]:
+ * thirteen 3x3 convolutions + ReLU + four 2x2 max-pools — fcd_conv2d_fwd / fcd_bn_act_fwd with scale == NULL / fcd_maxpool2_fwd)
+ * runs on ONE batch whose first half holds the masked target images and whose second half the masked generated images; f is a
+ * split NHWC feature tensor of 2*npix pixels, `half_elems` = element offset of the second half.  fwd: *acc += sum (a - b)^2
+ * (double, caller zero-initialises).  bwd: grad[first half] (+)= g*(a - b), grad[second half] (+)= -g*(a - b) with
+ * g = *gout * scale (scale = 2 * weight / element count), fp32 NHWC with pitch grad_ld. */
+int fcd_mse_halves_fwd(const void* f_hi, const void* f_lo, int f_ld, long long half_elems, long long npix, int Cp, double* acc,
+                       void* stream);
+int fcd_mse_halves_bwd(const void* f_hi, const void* f_lo, int f_ld, long long half_elems, long long npix, int Cp,
+                       const float* gout, float scale, float* grad, int grad_ld, long long grad_half_elems, int accumulate,
+                       void* stream);
+
 /* ---- rasters either side of the hot path ------------------------------------------------------
  * All pointers are device pointers.  geom is int[n_tiles][6], one row per tile of the grid, computed once on the host
  * (fcdgan_b200.raster.TileGrid = the geometry of GDALDataset.slice_assign, data_utils.py:151-176); items is int[B], the tile
@@ -281,20 +293,6 @@ int fcd_tiles_scatter(const float* tiles, const int* geom, const int* items, int
  * counts[i*2+j] += #{centre-crop pixels : int16(ref) == gt_map[i] && (cmap > thresh) == pre_map[j]}; counts is int64[4]. */
 int fcd_confusion_accumulate(const float* cmap, const float* ref, const int* geom, const int* items, int B, int patch_w,
                              int patch_h, float thresh, int gt0, int gt1, int pre0, int pre1, long long* counts, void* stream);
-
-/* bring-up probe for the tcgen05 shared-memory descriptor semantics (scripts/gpu_probe.py); not on the product path */
-int fcd_debug_umma_probe(const void* a, const void* b, float* d, int a_rows, int b_rows, int a_blocks, int b_blocks,
-                         int mn_major, int n, int ksteps, int a_shift_rows, int a_base_offset, int b_shift_rows,
-                         int b_base_offset, int a_sbo, int b_sbo, int a_lbo, int a_kstep, void* stream);
-
-/* tcgen05.mma issue-rate micro-benchmark (scripts/umma_bench.py): cycles for `iters` x 4 k-steps of UMMA(s) with the given
- * shape / major-ness / descriptor geometry, operands resident in shared memory; cycles[grid].  Not on the product path. */
-int fcd_debug_umma_bench(int mn_major, int n1, int n2, int a_sbo, int a_lbo, int a_kstep, int a_shift, int a2_off, int b_sbo,
-                         int b_lbo, int b_kstep, int stage_stride, int stages, int b_off, int iters, int a_tmem, int grid,
-                         long long* cycles, void* stream);
-
-/* compile-time UMMA "programs" (operand-reuse experiments, scripts/umma_bench2.py; the list is in probe_tc.cu) */
-int fcd_debug_umma_prog(int prog, int iters, int a_sbo, int grid, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

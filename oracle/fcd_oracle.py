@@ -7,7 +7,7 @@ and only as the checker / CPU baseline; the product path (fcdgan_b200) never doe
 Pinning: the reference has no tests and no golden vectors; this port is pinned against
 outputs of the UNMODIFIED reference modules imported from /root/reference in the build container
 (`oracle/make_golden.py` -> `tests/golden/*.pt`, checked by `tests/test_oracle_golden.py`), and, where the
-reference is mounted, live against it (`tests/test_oracle_vs_reference.py`).
+reference is mounted, live against it on fresh seeds (`tests/test_oracle_vs_reference.py`).
 
 The arithmetic itself lives in PyTorch (un-pinned by the reference, README.md:9); here torch 2.11 CPU.
 Every function cites the reference lines it restates.  Parameters are plain dicts keyed by the reference's
@@ -331,6 +331,68 @@ def cgenerator_loss(t: Tensor, g: Tensor, cmap: Tensor) -> Tuple[Tensor, Tensor]
     m = 1 - cmap
     ssim_loss = 1 - ms_ssim(t * m, g * m, data_range=1.0)
     return gen, ssim_loss
+
+
+# --------------------------------------------------------------------------------------------------
+# perception loss (Loss.py:17-61) — SURVEY.md §8(f) N1
+# --------------------------------------------------------------------------------------------------
+VGG16_FEATURES_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]   # torchvision cfg "D"
+VGG_FEATURE_LAYERS = [29, 22, 15, 8, 3]      # Loss.py:30
+
+
+def vgg16_features(seed: int = 1234):
+    """torchvision's `vgg16(weights=None).features` under a fixed seed, frozen, eval — the stand-in for the ImageNet weights
+    the reference downloads at Loss.py:25 (no network here).  oracle/ref_import.py rebinds `Loss.vgg16` to the same
+    construction, so reference, oracle and CUDA path see identical weights."""
+    import torchvision
+
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    net = torchvision.models.vgg16(weights=None).features.eval()
+    torch.random.set_rng_state(g)
+    for p in net.parameters():
+        p.requires_grad = False
+    return net
+
+
+def vgg_feature_mse(vgg_sd: SD, x: Tensor, y: Tensor, layers: List[int], scale: float) -> Tensor:
+    """Loss.py:44-48 / 56-59: run x and y through features[0..max(layers)], summing MSE(x, y) / scale at `layers`.
+    `vgg_sd`: state_dict of vgg16.features (keys "0.weight", "0.bias", "2.weight", ...)."""
+    total = 0
+    i = 0
+    for v in VGG16_FEATURES_CFG:
+        if v == "M":
+            x, y = F.max_pool2d(x, 2), F.max_pool2d(y, 2)
+            i += 1
+        else:
+            w, b = vgg_sd[f"{i}.weight"].to(x.dtype), vgg_sd[f"{i}.bias"].to(x.dtype)
+            x, y = F.conv2d(x, w, b, padding=1), F.conv2d(y, w, b, padding=1)
+            i += 1                                   # the ReLU layer
+            x, y = F.relu(x), F.relu(y)
+            if i in layers:
+                total = total + F.mse_loss(x, y) / scale
+            i += 1
+        if i > max(layers):
+            break
+    return total
+
+
+def perception_loss(vgg_sd: SD, target: Tensor, generate: Tensor, cmask: Tensor, feature_layer: int = 1,
+                    per_band: bool = False) -> Tensor:
+    """PerceptionLoss.forward, Loss.py:38-61."""
+    feature_layer = min(max(feature_layer, 1), 5)                      # Loss.py:32-33
+    layers = VGG_FEATURE_LAYERS[:feature_layer]
+    n = len(layers)
+    if not per_band:                                                   # Loss.py:40-48
+        m = 1 - cmask.repeat((1, 3, 1, 1))
+        return vgg_feature_mse(vgg_sd, target[:, 0:3] * m, generate[:, 0:3] * m, layers, n)
+    C = target.shape[1]                                                # Loss.py:50-60
+    total = 0
+    for b in range(C):
+        x = (target[:, b].unsqueeze(1) * (1 - cmask)).repeat((1, 3, 1, 1))
+        y = (generate[:, b].unsqueeze(1) * (1 - cmask)).repeat((1, 3, 1, 1))
+        total = total + vgg_feature_mse(vgg_sd, x, y, layers, n * C)
+    return total
 
 
 def region_loss(cmap: Tensor, region: Tensor, kind: str) -> Tensor:

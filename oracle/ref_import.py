@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference modules (Module.py, Loss.py, ssim.py) from /root/reference.
+"""Import the UNMODIFIED reference modules (Module.py, Loss.py, ssim.py).
 
-TEST INFRASTRUCTURE ONLY.  Works only where /root/reference is mounted (the build container); it is used by
-oracle/make_golden.py to generate tests/golden/*.pt and by tests that pin the oracle port against the real
-reference.  Nothing on the product path, in `-m gpu` tests, smoke() or bench.py may import this.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Source of the files: /root/reference where it is mounted (the build container —
+oracle/make_golden.py generates tests/golden/*.pt from it and tests pin the oracle port against it), else the byte-identical
+staged copy `oracle/_ref/` that oracle/build_ref.py makes (git-ignored, travels to the GPU box like a built .so), which is what
+`bench.py --impl reference` / `cpu_baseline` time on the GPU box's host cores.  Nothing on the product path imports this,
+and nothing that runs on the GPU box reads /root/reference.
 
 Two shims:
   1. `osgeo` stub package (GDAL is not installed; CommonFunc.py:17-19 imports it at module scope);
@@ -12,22 +14,39 @@ Two shims:
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_DIR = os.environ.get("FCD_REFERENCE_DIR", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shim")
+STAGED_DIR = os.path.join(_HERE, "_ref")
+_SHIM = os.path.join(_HERE, "_shim")
+
+
+def source_dir(prefer_staged: bool = False):
+    """Directory the reference files are imported from: the mounted reference, else the staged copy, else None
+    (`prefer_staged`: the staged copy first — bench.py, which must not read /root/reference at run time)."""
+    for d in ((STAGED_DIR, REFERENCE_DIR) if prefer_staged else (REFERENCE_DIR, STAGED_DIR)):
+        if all(os.path.isfile(os.path.join(d, f)) for f in ("Module.py", "Loss.py", "ssim.py", "CommonFunc.py")):
+            return d
+    return None
 
 
 def available() -> bool:
+    """The mounted reference (build container) — the live-pinning tests and golden generators need this one."""
     return os.path.isfile(os.path.join(REFERENCE_DIR, "Module.py"))
 
 
-def load():
+def importable() -> bool:
+    return source_dir() is not None
+
+
+def load(prefer_staged: bool = False):
     """Returns (Module, Loss, ssim) reference python modules."""
-    if not available():
-        raise RuntimeError(f"reference not mounted at {REFERENCE_DIR}")
+    src = source_dir(prefer_staged)
+    if src is None:
+        raise RuntimeError(f"reference neither mounted at {REFERENCE_DIR} nor staged at {STAGED_DIR} (oracle/build_ref.py)")
     if _SHIM not in sys.path:
         sys.path.insert(0, _SHIM)
-    if REFERENCE_DIR not in sys.path:
-        sys.path.append(REFERENCE_DIR)
+    if src not in sys.path:
+        sys.path.append(src)
     import torch
     import torchvision
 

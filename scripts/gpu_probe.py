@@ -38,7 +38,7 @@ def umma_probe():
         B = (torch.randint(-4, 5, (b_blocks, b_rows, 64), generator=g).float()).to(dev)
         Ab, Bb = A.to(torch.bfloat16).contiguous(), B.to(torch.bfloat16).contiguous()
         D = torch.full((128, n), float("nan"), device=dev)
-        _lib.call("fcd_debug_umma_probe", Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), a_rows, b_rows, a_blocks,
+        _lib.call_probe("fcd_debug_umma_probe", Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), a_rows, b_rows, a_blocks,
                   b_blocks, mn_major, n, ksteps, a_shift, a_bo, b_shift, b_bo, a_sbo, b_sbo, 0, 0, None)
         torch.cuda.synchronize()
         return A.double(), B.double(), D.double()

@@ -12,7 +12,7 @@ g = torch.Generator().manual_seed(3)
 def run(A, B, n, ksteps, mn, a_shift=0, a_sbo=0, a_lbo=0, a_kstep=0):
     Ab, Bb = A.to(torch.bfloat16).contiguous().to(dev), B.to(torch.bfloat16).contiguous().to(dev)
     D = torch.full((128, n), float("nan"), device=dev)
-    _lib.call("fcd_debug_umma_probe", Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), A.shape[1], B.shape[1], A.shape[0], B.shape[0],
+    _lib.call_probe("fcd_debug_umma_probe", Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), A.shape[1], B.shape[1], A.shape[0], B.shape[0],
               mn, n, ksteps, a_shift, 0, 0, 0, a_sbo, 0, a_lbo, a_kstep, None)
     torch.cuda.synchronize()
     return D.double().cpu()

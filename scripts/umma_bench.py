@@ -9,7 +9,7 @@ ITERS = 2000
 def run(name, grid=1, mn=0, n1=64, n2=0, a_sbo=1024, a_lbo=16, a_kstep=32, a_shift=0, a2_off=16384, b_sbo=1024, b_lbo=16,
         b_kstep=32, stage_stride=49152, stages=4, b_off=32768, a_tmem=0):
     cyc = torch.zeros(grid, dtype=torch.int64, device=dev)
-    _lib.call("fcd_debug_umma_bench", mn, n1, n2, a_sbo, a_lbo, a_kstep, a_shift, a2_off, b_sbo, b_lbo, b_kstep, stage_stride,
+    _lib.call_probe("fcd_debug_umma_bench", mn, n1, n2, a_sbo, a_lbo, a_kstep, a_shift, a2_off, b_sbo, b_lbo, b_kstep, stage_stride,
               stages, b_off, ITERS, a_tmem, grid, cyc.data_ptr(), None)
     torch.cuda.synchronize()
     c = cyc.cpu().double()

@@ -30,7 +30,7 @@ PROGS = [
 for grid in (1,):
     for i, (name, ideal) in enumerate(PROGS):
         cyc = torch.zeros(grid, dtype=torch.int64, device=dev)
-        _lib.call("fcd_debug_umma_prog", i, ITERS, 1024, grid, cyc.data_ptr(), None)
+        _lib.call_probe("fcd_debug_umma_prog", i, ITERS, 1024, grid, cyc.data_ptr(), None)
         torch.cuda.synchronize()
         per = cyc.double().mean().item() / (ITERS * 4)
         print(f"{i:2d} {name:58s} {per:7.1f} cyc/k-step   ideal {ideal:4d}  -> {ideal / per * 100:5.1f} %", flush=True)

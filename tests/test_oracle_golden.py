@@ -84,6 +84,53 @@ def test_losses():
     assert rel_err(cm3.grad, f["region_dcmap"]) < 1e-4
 
 
+def _vgg_sd():
+    net = O.vgg16_features(1234)
+    return net, {k: v for k, v in net.state_dict().items()}
+
+
+def test_perception():
+    """Perception loss (Loss.py:17-61) against the unmodified reference's PerceptionLoss / CNetLoss /
+    CGeneratorLoss run with the same seeded random-init VGG16 (oracle/make_golden_perception.py)."""
+    f = load_golden("perception.pt")
+    net, sd = _vgg_sd()
+    chk = float(sum(p.double().abs().sum() for p in net.parameters()))
+    assert abs(chk - f["vgg_checksum"]) < 1e-6 * chk, "this torchvision initialises VGG16 differently from the fixture's"
+    for key, layers, per_band in (("perband", 1, True), ("rgb5", 5, False)):
+        d = f[key]
+        g = d["g"].clone().requires_grad_(True)
+        cmap = d["cmap"].clone().requires_grad_(True)
+        v = O.perception_loss(sd, d["t"], g, cmap, layers, per_band)
+        assert abs(v.item() - d["value"]) <= 1e-4 * abs(d["value"]), key
+        v.backward()
+        assert rel_err(g.grad, d["dg"]) < 1e-4 and rel_err(cmap.grad, d["dcmap"]) < 1e-4, key
+    # inside CNetLoss (per band, weight 0.4) and CGeneratorLoss (RGB, two layers, weight 0.5)
+    d = f["cnet"]
+    g = d["g"].clone().requires_grad_(True)
+    cmap = d["cmap"].clone().requires_grad_(True)
+    gl, l1, sl = O.cnet_loss(d["t"], g, cmap)
+    perc = O.perception_loss(sd, d["t"], g, cmap, 1, True)
+    for got, ref in zip((gl, l1, perc, sl), d["values"]):
+        assert abs(got.item() - ref) <= 1e-4 * max(abs(ref), 1e-6)
+    (gl + 0.65 * l1 + 0.4 * perc + 0.3 * sl).backward()
+    assert rel_err(g.grad, d["dg"]) < 1e-4 and rel_err(cmap.grad, d["dcmap"]) < 1e-4
+    g2 = d["g"].clone().requires_grad_(True)
+    cmap2 = d["cmap"].clone().requires_grad_(True)
+    gl2, sl2 = O.cgenerator_loss(d["t"], g2, cmap2)
+    perc2 = O.perception_loss(sd, d["t"], g2, cmap2, 2, False)
+    for got, ref in zip((gl2, sl2, perc2), f["cgen"]["values"]):
+        assert abs(got.item() - ref) <= 1e-4 * max(abs(ref), 1e-6)
+    (gl2 + 0.5 * perc2).backward()
+    assert rel_err(g2.grad, f["cgen"]["dg"]) < 1e-4 and rel_err(cmap2.grad, f["cgen"]["dcmap"]) < 1e-4
+    # hard mask (generator_mask_switch=True, Loss.py:75,89-90)
+    g3 = d["g"].clone().requires_grad_(True)
+    hard = (torch.sign(d["cmap"] - 0.5) + 1) / 2
+    p3 = O.perception_loss(sd, d["t"], g3, hard, 1, True)
+    assert abs(p3.item() - f["cnet_hard"]["value"]) <= 1e-4 * f["cnet_hard"]["value"]
+    p3.backward()
+    assert rel_err(g3.grad, f["cnet_hard"]["dg"]) < 1e-4
+
+
 def test_ssim_family():
     f = load_golden("losses.pt")
     X, Y = f["X"], f["Y"]
