@@ -170,7 +170,7 @@ def _loss_list(out):
     import torch
 
     if isinstance(out, dict):
-        keys = [k for k in ("generator_loss", "Loss", "NetLoss", "d_loss", "s_loss") if k in out]
+        keys = [k for k in ("Loss", "NetLoss", "d_loss", "s_loss") if k in out]      # the order oracle/ref_steps.py returns them in
         return [out[k] for k in keys]
     if torch.is_tensor(out):
         return [out]

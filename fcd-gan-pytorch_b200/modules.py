@@ -25,6 +25,16 @@ def _check_input(x: torch.Tensor, channels: int, what: str):
         raise ValueError(f"{what}: expected (B, {channels}, H, W), got {tuple(x.shape)}")
 
 
+def _check_bn_width(c: int, what: str):
+    """Widths of BatchNorm-ed tensors the reduction kernels take: the channel count, padded to a multiple of 64, must be a
+    power of two <= 2048 (fcd_bn_stats / fcd_bn_act_bwd_reduce walk 256-thread blocks over Cp / 8 channel groups).  Every
+    width of the reference's networks qualifies (64 ... 1024, Module.py:101-111, 195-210)."""
+    cp = E.pad_ch(c)
+    if c < 1 or cp > 2048 or cp & (cp - 1):
+        raise ValueError(f"{what}: unsupported channel count {c} (padded to {cp}): BatchNorm-ed tensors need a padded channel "
+                         "count that is a power of two between 64 and 2048")
+
+
 # ------------------------------------------------------------------------------------------------
 # engine-level building blocks (operate on internal NHWC activations)
 # ------------------------------------------------------------------------------------------------
@@ -56,6 +66,8 @@ class DoubleConv(nn.Module):
         super().__init__()
         if not mid_channels:
             mid_channels = out_channels
+        _check_bn_width(mid_channels, "DoubleConv(mid_channels)")
+        _check_bn_width(out_channels, "DoubleConv(out_channels)")
         self.double_conv = nn.Sequential(
             nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1),
             nn.BatchNorm2d(mid_channels),
@@ -103,6 +115,10 @@ class Up(nn.Module):
     def __init__(self, in_channels, out_channels, bilinear=False):
         super().__init__()
         self.bilinear = bool(bilinear)
+        if in_channels % 128:
+            raise ValueError(f"Up: unsupported channel count {in_channels}: the skip and the upsampled tensor (in_channels / 2 "
+                             "each) share one NHWC concatenation buffer in 64-channel slots, so in_channels must be a multiple "
+                             "of 128 (the reference uses 256 ... 2048, Module.py:107-110)")
         if bilinear:
             self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
             self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
@@ -143,6 +159,9 @@ class OutConv(nn.Module):
 
     def __init__(self, in_channels, out_channels):
         super().__init__()
+        if in_channels > 128 or out_channels > 4:
+            raise ValueError(f"OutConv({in_channels}, {out_channels}): the fused 1x1 + sigmoid kernel takes at most 128 input and 4 "
+                             "output channels (the reference uses 128 -> 1, Module.py:111)")
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
         self.sigmoid = nn.Sigmoid()
 
@@ -241,6 +260,7 @@ class ResidualBlock(nn.Module):
 
     def __init__(self, channels):
         super().__init__()
+        _check_bn_width(channels, "ResidualBlock")
         self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
         self.bn1 = nn.BatchNorm2d(channels)
         self.prelu = nn.PReLU()

@@ -1,0 +1,111 @@
+"""Runner of tests/test_dp_gpu.py (launched with torchrun, one rank per GPU, NCCL): an N-rank sharded iteration with
+`parallel.GradSync` must give every rank the gradients of the 1-rank full-batch iteration.
+
+With BatchNorm in eval mode (running statistics) samples are independent, the losses are batch means and the shards are equal,
+so mean-over-ranks of the shard gradients IS the full-batch gradient; what is left is fp32 summation order (the weight-gradient
+reductions use fp32 atomics; the all-reduce sums in another order than one big batch would): tolerance 2e-5 of each tensor's
+maximum.  Checked for the eager exchange (`GradSync.on_grads`) and for the CUDA-graph form bench.py uses at N > 1
+(`graph.YieldingStep`: graphs cut at the exchange points, NCCL calls between them)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fcdgan_b200 as fb  # noqa: E402
+from fcdgan_b200 import parallel as P  # noqa: E402
+from fcdgan_b200.graph import YieldingStep  # noqa: E402
+from fcdgan_b200.steps import drive  # noqa: E402
+
+C, H, W, PER_RANK = 4, 64, 56, 2
+
+
+def make_nets(dev):
+    torch.manual_seed(0)
+    netG = fb.Generator(C).to(dev).eval()
+    torch.manual_seed(1)
+    netD = fb.Discriminator_SRGAN_simple(C).to(dev).eval()
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():                      # non-trivial running statistics
+        for net in (netG, netD):
+            for k, v in net.state_dict().items():
+                if "running_var" in k:
+                    v.copy_((0.5 + torch.rand(v.shape, generator=g)).to(dev))
+                elif "running_mean" in k:
+                    v.copy_((0.2 * torch.randn(v.shape, generator=g)).to(dev))
+    return netG, netD
+
+
+def make_gen(netG, netD):
+    def gen(x, y, cmap):
+        zero = torch.zeros_like(cmap)
+        y_fake = netG(x)
+        gl, _, _, _ = fb.losses._MaskedRecon.apply(y, y_fake, zero, fb.losses.LOSS_L1, False)
+        netG.zero_grad()
+        gl.backward()
+        yield netG, False
+        c_out = netD(fb.soft_mask(x, cmap), fb.soft_mask(y, cmap))
+        nc_out = netD(fb.soft_mask(x, cmap), fb.soft_mask(x, cmap))
+        dl = 1 + fb.mean(nc_out) - fb.mean(c_out)
+        netD.zero_grad()
+        dl.backward()
+        yield netD, True
+        return gl, dl
+    return gen
+
+
+def grads(*nets):
+    return [(k, p.grad.detach().clone()) for n in nets for k, p in n.named_parameters()]
+
+
+def main():
+    local = P.init_from_env("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", local)
+    fb.set_precision("parity")
+    B = PER_RANK * world
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g)
+    y = x + 0.3 * torch.randn(B, C, H, W, generator=g)
+    cmap = 0.3 * torch.rand(B, 1, H, W, generator=g)
+    sl = P.shard_batch(B, rank, world)
+    xs, ys, cs = (t[sl].to(dev) for t in (x, y, cmap))
+    # 1-rank full batch (every rank computes it for itself; no communication)
+    netG, netD = make_nets(dev)
+    gl_full, dl_full = drive(make_gen(netG, netD)(x.to(dev), y.to(dev), cmap.to(dev)))
+    want = grads(netG, netD)
+    # N-rank sharded, eager exchange
+    netG, netD = make_nets(dev)
+    P.broadcast_parameters([netG, netD])
+    sync = P.GradSync()
+    gl, dl = drive(make_gen(netG, netD)(xs, ys, cs), sync.on_grads)
+    got_eager = grads(netG, netD)
+    # N-rank sharded, CUDA graphs cut at the exchange points
+    step = YieldingStep(make_gen(netG, netD), sync, [xs, ys, cs], warmup=2)
+    assert len(step.graphs) == 3
+    step()
+    torch.cuda.synchronize()
+    got_graph = grads(netG, netD)
+    worst = 0.0
+    for what, got in (("eager", got_eager), ("graphs", got_graph)):
+        for (k, a), (_, b) in zip(got, want):
+            scale = b.abs().max().item()
+            if scale < 1e-7:
+                continue
+            err = (a - b).abs().max().item() / scale
+            worst = max(worst, err)
+            assert err < 2e-5, f"rank {rank} [{what}] {k}: {err:.3g}"
+    losses = torch.stack([gl.detach(), dl.detach()])
+    dist.all_reduce(losses)
+    losses /= world
+    assert abs(losses[0].item() - gl_full.item()) < 1e-6 * max(1, abs(gl_full.item())), (losses, gl_full)
+    assert abs(losses[1].item() - dl_full.item()) < 1e-6 * max(1, abs(dl_full.item())), (losses, dl_full)
+    dist.barrier()
+    if rank == 0:
+        print(f"DP_EQUIV_OK world={world} worst_rel_err={worst:.2e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

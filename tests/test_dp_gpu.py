@@ -1,0 +1,21 @@
+"""2-GPU equivalence of the data-parallel layer on real NCCL (SURVEY.md §4 last row, §8(e)): an N-rank sharded iteration ==
+the 1-rank full-batch iteration, for the eager exchange and for the CUDA-graph form (tests/_dp_equiv.py).  Needs >= 2 GPUs
+(`gpurun --gpus 2`); skipped on a 1-GPU box.  The host-side logic of the same code runs on gloo in tests/test_parallel.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_step_equals_full_batch_step():
+    env = dict(os.environ, FCD_DIST_TIMEOUT_S="120")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_dp_equiv.py")],
+                         capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
+    assert res.returncode == 0 and "DP_EQUIV_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])

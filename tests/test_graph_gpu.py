@@ -1,8 +1,12 @@
-"""The launch path bench.py uses at N = 1: a whole training iteration replayed from ONE CUDA graph
-(fcdgan_b200.graph.GraphedStep) must produce what the same iteration produces when issued eagerly — same losses, same
-parameters after several optimizer steps (up to the fp32 atomics of the weight-gradient reductions).  The segmented form
-used at N > 1 (graphs with eager NCCL calls in between) is exercised by the multi-GPU bench runs (profiles/README.md) and,
-for the exchange itself, by the gloo test of GradSync's pack / launch / wait / unpack phases (tests/test_parallel.py)."""
+"""The launch paths bench.py uses: a whole training iteration replayed from ONE CUDA graph (fcdgan_b200.graph.GraphedStep,
+N = 1) and the same iteration cut into several graphs at its gradient-exchange points (graph.YieldingStep, the N > 1 form —
+here on one GPU, where the exchange between the graphs is a no-op) must produce what the iteration produces when issued
+eagerly: same loss trajectory, same parameters after several optimizer steps.
+
+Tolerance of the loss trajectory: the weight-gradient reductions use fp32 atomics, so two EAGER runs from the same state are
+not bit-identical either; Adam / RMSprop turn a gradient element at that noise level into a full lr-sized step of either sign,
+and the losses of iterations 2, 3 inherit it.  The test measures that run-to-run spread (two eager runs) and holds the graph
+replays to max(3e-5, 4 x spread) relative — the first iteration, which no optimizer step precedes, to 1e-6."""
 import copy
 import re
 
@@ -10,7 +14,9 @@ import pytest
 import torch
 
 import fcdgan_b200 as fb
-from fcdgan_b200.graph import GraphedStep
+from fcdgan_b200 import engine as E
+from fcdgan_b200.graph import GraphedStep, YieldingStep
+from fcdgan_b200.parallel import GradSync
 from oracle import fcd_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -66,29 +72,58 @@ def _params(*nets):
     return [(k, p.detach().clone()) for n in nets for k, p in n.named_parameters() if not _NOISE_GRAD.fullmatch(k)]
 
 
-def test_graph_replay_matches_eager():
-    fb.set_precision("parity")
-    steps = 3
-    # eager run
+def _eager_run(steps):
     netG, netD, optG, optD, x, y, cmap, zero = _setup()
     seg_g, seg_d, seg_opt = _segments(netG, netD, optG, optD, zero)
-    eager_losses = []
+    losses = []
     for _ in range(steps):
         gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
         seg_opt(x, y, cmap)
-        eager_losses.append((gl.item(), dl.item()))
-    want = _params(netG, netD)
+        losses.append((gl.item(), dl.item()))
+    return losses, _params(netG, netD)
+
+
+@pytest.fixture(autouse=True)
+def _no_leaked_state():
+    """Graph capture allocates from a private pool and warms up on a side stream; nothing of it may outlive the test (the
+    eager workspace cache is dropped, so later tests cannot inherit a block that was first used on the side stream)."""
+    yield
+    E.clear_caches()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("form", ["whole", "segmented"])
+def test_graph_replay_matches_eager(form):
+    fb.set_precision("parity")
+    steps = 3
+    eager_losses, want = _eager_run(steps)
+    eager_again, _ = _eager_run(steps)
+    spread = max(abs(a - b) / max(1.0, abs(a)) for la, lb in zip(eager_losses, eager_again) for a, b in zip(la, lb))
+    tol = max(3e-5, 4 * spread)
     # graph run from the same initial state; the warm-up iterations of the capture advance the optimizers too, so the
     # initial state is restored after the capture
     netG, netD, optG, optD, x, y, cmap, zero = _setup()
     state = (copy.deepcopy(netG.state_dict()), copy.deepcopy(netD.state_dict()))
     seg_g, seg_d, seg_opt = _segments(netG, netD, optG, optD, zero)
-    def whole(x, y, cmap):
-        gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
-        seg_opt(x, y, cmap)
-        return gl, dl
+    if form == "whole":
+        def whole(x, y, cmap):
+            gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
+            seg_opt(x, y, cmap)
+            return gl, dl
 
-    step = GraphedStep(whole, [x, y, cmap], warmup=2)
+        step = GraphedStep(whole, [x, y, cmap], warmup=2)
+    else:
+        def gen(x, y, cmap):
+            gl = seg_g(x, y, cmap)
+            yield netG, False
+            dl = seg_d(x, y, cmap)
+            yield netD, True
+            seg_opt(x, y, cmap)
+            return gl, dl
+
+        step = YieldingStep(gen, GradSync(), [x, y, cmap], warmup=2)
+        assert len(step.graphs) == 3
     run = lambda: step()
     assert step.launches_per_replay > 50
     # restore IN PLACE (the graphs hold the parameter / optimizer-state addresses)
@@ -104,8 +139,9 @@ def test_graph_replay_matches_eager():
                         v.zero_()
     for i in range(steps):
         gl, dl = run()
-        assert abs(gl.item() - eager_losses[i][0]) <= 3e-4 * max(1.0, abs(eager_losses[i][0])), (i, gl.item(), eager_losses[i])
-        assert abs(dl.item() - eager_losses[i][1]) <= 3e-4 * max(1.0, abs(eager_losses[i][1])), (i, dl.item(), eager_losses[i])
+        t = 1e-6 if i == 0 else tol
+        assert abs(gl.item() - eager_losses[i][0]) <= t * max(1.0, abs(eager_losses[i][0])), (form, i, gl.item(), eager_losses[i], spread)
+        assert abs(dl.item() - eager_losses[i][1]) <= t * max(1.0, abs(eager_losses[i][1])), (form, i, dl.item(), eager_losses[i], spread)
     # Adam's / RMSprop's first steps move every element by ~lr (10 lr for RMSprop) * sign(gradient): an element whose gradient
     # is at the level of the weight-gradient reductions' atomic-order noise may take the other sign, so a few elements per tensor
     # can legitimately differ by a couple of step sizes.  The loss trajectory above is the tight check; here the bulk of every

@@ -75,3 +75,55 @@ def test_grad_sync_two_ranks_gloo(tmp_path):
     for i, (a, b) in enumerate(zip(g0, g1)):
         assert torch.equal(a, b)
         assert torch.allclose(a, torch.full_like(a, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
+
+
+def _step_gen(net, opt, x, y):
+    """a step body in the shape of fcdgan_b200.steps.*_gen: yields (network, wait) where the gradients are complete"""
+    loss = ((net(x) - y) ** 2).mean()
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    yield net, True
+    opt.step()
+    return loss
+
+
+def _worker_step(rank, world, port, out):
+    from fcdgan_b200.steps import drive
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    x, y = torch.randn(8, 3, 10, 10, generator=g), torch.randn(8, 4, 8, 8, generator=g)
+    torch.manual_seed(3)
+    full = torch.nn.Conv2d(3, 4, 3)
+    torch.manual_seed(50 + rank)
+    mine = torch.nn.Conv2d(3, 4, 3)
+    with torch.no_grad():
+        if rank == 0:
+            for a, b in zip(mine.parameters(), full.parameters()):
+                a.copy_(b)
+    P.broadcast_parameters([mine])
+    opt_full, opt_mine = torch.optim.SGD(full.parameters(), lr=0.1), torch.optim.SGD(mine.parameters(), lr=0.1)
+    sync = P.GradSync()
+    sl = P.shard_batch(8, rank, world)
+    for _ in range(3):
+        drive(_step_gen(full, opt_full, x, y))                            # 1-rank full batch, no exchange
+        drive(_step_gen(mine, opt_mine, x[sl], y[sl]), sync.on_grads)     # sharded, exchange at the yield
+    err = max((a - b).abs().max().item() for a, b in zip(mine.parameters(), full.parameters()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, err)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_step_through_on_grads_equals_full_batch_gloo(tmp_path):
+    """N-rank sharded optimizer steps driven through the step generators' exchange points (steps.drive + GradSync.on_grads)
+    track the 1-rank full-batch steps (no BatchNorm in the toy net, so the equivalence is exact up to summation order)."""
+    world = 2
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_step, args=(world, _free_port(), out), nprocs=world, join=True)
+    errs = torch.load(out, weights_only=False)
+    assert max(errs) < 1e-6, errs

@@ -1,0 +1,141 @@
+"""Parity at PRODUCTION shapes (the golden fixtures pin the arithmetic at toy shapes; persistent-CTA tile schedules, split-K
+factors and round-robin K sweeps only take their production values here): BASELINE's 13 x 256 x 256 tiles in TRAIN mode with
+B >= 2 — forward, input-independent parameter gradients and BatchNorm running statistics against the CPU oracle (pinned to
+the unmodified reference by tests/test_oracle_golden.py and tests/test_oracle_vs_reference.py) — and the Segmentor at the demos'
+own tile sizes 220 x 220 x 4 (Demo_USSS.py:57) and 200 x 200 x 4 (Demo_RSSS.py:36), whose odd pooling pyramids
+(220 -> 110 -> 55 -> 27 -> 13, 200 -> 100 -> 50 -> 25 -> 12) exercise floor pooling + F.pad at every decoder level.
+
+Tolerances: outputs 1e-3 of the tensor maximum (north-star bar); end-to-end parameter gradients in whole-tensor relative L2.
+At these sizes every BatchNorm sees thousands of values, so the conditioning argument that justified 5e-2 for the Segmentor /
+Discriminator at toy shapes (tests/test_networks_gpu.py) no longer applies: 1e-2 here (Generator 3e-3)."""
+import pytest
+import torch
+
+import fcdgan_b200 as fb
+from oracle import fcd_oracle as O
+from tests._util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUT_TOL = 1e-3
+
+
+def _pair(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g)
+    y = x + 0.3 * torch.randn(B, C, H, W, generator=g)
+    y[:, :, H // 4:H // 2, W // 3:2 * W // 3] = torch.randn(B, C, H // 2 - H // 4, 2 * W // 3 - W // 3, generator=g)
+    return x, y
+
+
+def _grad_report(net, sd, l2tol, what):
+    """Per-tensor relative L2 (tensors with >= 64 elements and a non-vanishing reference gradient), global cosine / norm."""
+    dot = n1 = n2 = 0.0
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        assert p.grad is not None, f"{what}: no gradient for {k}"
+        g, r = p.grad.detach().double().cpu().flatten(), sd[k].grad.double().flatten()
+        dot += float(g @ r); n1 += float(g @ g); n2 += float(r @ r)
+        if r.abs().max().item() < 1e-4 * max(1.0, (n2 ** 0.5)) and r.abs().max().item() < 1e-5:
+            continue                                   # analytically zero (conv bias in front of a train-mode BatchNorm)
+        if r.numel() >= 64 and r.norm() > 1e-6 * (n2 ** 0.5 + 1e-30):
+            l2 = float((g - r).norm() / r.norm())
+            if l2 > worst[1]:
+                worst = (k, l2)
+    cos = dot / (n1 ** 0.5 * n2 ** 0.5)
+    ratio = n1 ** 0.5 / n2 ** 0.5
+    print(f"[{what}] worst per-tensor rel-L2 {worst[1]:.2e} ({worst[0]}), cosine {1 - cos:.1e} from 1, norm ratio {ratio:.6f}")
+    assert worst[1] < l2tol, f"{what}: grad {worst[0]} rel-L2 {worst[1]:.3g} >= {l2tol}"
+    assert cos > 1 - l2tol ** 2 and abs(ratio - 1) < l2tol, (what, cos, ratio)
+
+
+def _running(net, sd, what):
+    own = net.state_dict()
+    for k, v in sd.items():
+        if "running" in k:
+            assert rel_err(own[k].float(), v.detach().float()) < 1e-4, (what, k)
+
+
+def test_generator_train_batch4_full_tile():
+    fb.set_precision("parity")
+    C, B = 13, 4
+    x, _ = _pair(B, C, 256, 256, 501)
+    sd0 = O.make_state_dict(O.generator_spec(C), 11)
+    net = fb.Generator(C); net.load_state_dict(sd0); net.to(DEV).train()
+    r = torch.randn(B, C, 256, 256, generator=torch.Generator().manual_seed(502))
+    out = net(x.to(DEV))
+    (out * r.to(DEV)).sum().backward()
+    sd = O.clone_sd(sd0, requires_grad=True)
+    out_o = O.generator(sd, x, train=True)
+    (out_o * r).sum().backward()
+    assert rel_err(out, out_o) < OUT_TOL, rel_err(out, out_o)
+    _grad_report(net, sd, 3e-3, "G 13x256x256 B=4 train")
+    _running(net, sd, "G")
+
+
+def test_discriminator_train_batch4_full_tile():
+    fb.set_precision("parity")
+    C, B = 13, 4
+    x, y = _pair(B, C, 256, 256, 511)
+    sd0 = O.make_state_dict(O.discriminator_spec(C), 13)
+    net = fb.Discriminator_SRGAN_simple(C); net.load_state_dict(sd0); net.to(DEV).train()
+    r = torch.randn(B, generator=torch.Generator().manual_seed(512))
+    xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)      # gradient path into the inputs (-> cmap -> S)
+    out = net(xd, yd)
+    (out * r.to(DEV)).sum().backward()
+    sd = O.clone_sd(sd0, requires_grad=True)
+    xo, yo = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    out_o = O.discriminator(sd, xo, yo, train=True)
+    (out_o * r).sum().backward()
+    assert rel_err(out, out_o) < OUT_TOL
+    assert rel_l2(xd.grad, xo.grad) < 1e-2 and rel_l2(yd.grad, yo.grad) < 1e-2, (rel_l2(xd.grad, xo.grad), rel_l2(yd.grad, yo.grad))
+    _grad_report(net, sd, 1e-2, "D 13x256x256 B=4 train")
+    _running(net, sd, "D")
+    # the data-input (im2col) path at the same shape
+    net.zero_grad()
+    out2 = net(x.to(DEV), y.to(DEV))
+    assert rel_err(out2, out_o) < OUT_TOL
+    (out2 * r.to(DEV)).sum().backward()
+    _grad_report(net, sd, 1e-2, "D 13x256x256 B=4 train, im2col first layer")
+
+
+@pytest.mark.parametrize("C,H,W,B", [(13, 256, 256, 2), (4, 220, 220, 2), (4, 200, 200, 2)])
+def test_segmentor_train_production_tiles(C, H, W, B):
+    fb.set_precision("parity")
+    x, y = _pair(B, C, H, W, 521 + H)
+    sd0 = O.make_state_dict(O.segmentor_spec(C, 1, True), 12)
+    net = fb.Segmentor(C, 1, True); net.load_state_dict(sd0); net.to(DEV).train()
+    r = torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(522))
+    cmap = net(x.to(DEV), y.to(DEV))
+    (cmap * r.to(DEV)).sum().backward()
+    sd = O.clone_sd(sd0, requires_grad=True)
+    cmap_o = O.segmentor(sd, x, y, bilinear=True, train=True)
+    (cmap_o * r).sum().backward()
+    err = rel_err(cmap, cmap_o)
+    print(f"[S {C}x{H}x{W} B={B}] change-density map max rel err {err:.2e}")
+    assert err < OUT_TOL                                     # the north-star parity bar
+    _grad_report(net, sd, 1e-2, f"S {C}x{H}x{W} B={B} train")
+    _running(net, sd, "S")
+
+
+def test_loss_values_at_full_tile():
+    """CNetLoss (masked L1, mean|cmap|, MS-SSIM) and the RSSS region terms at 13 x 256 x 256, B = 4, values and gradients."""
+    import torch.nn as nn
+    B, C, H, W = 4, 13, 256, 256
+    t, gen0 = _pair(B, C, H, W, 531)
+    cm0 = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(532))
+    region = (torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(533)) > 0.6).float()
+    g = gen0.to(DEV).requires_grad_(True)
+    cm = cm0.to(DEV).requires_grad_(True)
+    gl, l1, _, sl = fb.CNetLoss(channel=C)(t.to(DEV), g, cm)
+    r1 = fb.region_loss(cm, region.to(DEV), nn.L1Loss())
+    r2 = fb.region_loss(cm, 1 - region.to(DEV), nn.MSELoss())
+    (gl + 0.65 * l1 + 0.3 * sl + 0.02 * r1 + 2 * r2).backward()
+    go = gen0.clone().requires_grad_(True)
+    co = cm0.clone().requires_grad_(True)
+    gl_o, l1_o, sl_o = O.cnet_loss(t, go, co)
+    r1_o, r2_o = O.region_loss(co, region, "l1"), O.region_loss(co, 1 - region, "mse")
+    (gl_o + 0.65 * l1_o + 0.3 * sl_o + 0.02 * r1_o + 2 * r2_o).backward()
+    for a, b in ((gl, gl_o), (l1, l1_o), (sl, sl_o), (r1, r1_o), (r2, r2_o)):
+        assert abs(a.item() - b.item()) <= 1e-4 * max(abs(b.item()), 1e-3), (a.item(), b.item())
+    assert rel_err(g.grad, go.grad) < 2e-4 and rel_err(cm.grad, co.grad) < 2e-4
