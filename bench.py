@@ -332,6 +332,12 @@ def run_ours(args):
                 from fcdgan_b200.graph import GraphedStep
                 gstep = GraphedStep(lambda *a: _loss_list(drive(genfn(*a))), data, warmup=3)
                 graph_note = "whole iteration captured in one CUDA graph (fcdgan_b200.graph.GraphedStep)"
+            elif args.collectives == "captured":
+                # experiment: the NCCL all-reduces captured INSIDE the one graph (round 1: hung on this stack)
+                from fcdgan_b200.graph import GraphedStep
+                gstep = GraphedStep(lambda *a: _loss_list(drive(genfn(*a), sync.on_grads)), data, warmup=3,
+                                    capture_error_mode="thread_local")
+                graph_note = "whole iteration INCLUDING the NCCL all-reduces captured in one CUDA graph"
             else:
                 from fcdgan_b200.graph import YieldingStep
                 gstep = YieldingStep(genfn, sync, data, warmup=3)
@@ -668,7 +674,9 @@ def main():
     ap.add_argument("--precision", choices=["parity", "fast"], default="parity")
     ap.add_argument("--impl", choices=["ours", "reference", "cudnn"], default="ours")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto", help="capture the iteration in a CUDA graph")
-    ap.add_argument("--streams", type=int, default=2, help="engine streams (independent branches / weight gradients run concurrently)")
+    ap.add_argument("--collectives", choices=["eager", "captured"], default="eager",
+                    help="N > 1: NCCL calls issued eagerly between CUDA graphs (default) or captured inside one graph (experiment)")
+    ap.add_argument("--streams", type=int, default=1, help="engine streams (independent branches / weight gradients run concurrently)")
     ap.add_argument("--max-seconds", type=float, default=0.0, help="hard-exit the process after this many seconds (0 = off at N = 1, 900 at N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")

@@ -210,12 +210,22 @@ class PackedAct:
 
 
 # --------------------------------------------------------------------------------------------------
-_workspace: Dict[torch.device, torch.Tensor] = {}
+_workspace: Dict[tuple, torch.Tensor] = {}      # (device, stream) -> split-K scratch of the weight-gradient kernels
+_side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
 _weight_epoch = 0     # bumped whenever parameters may have changed WITHOUT their version counter moving (graph replay)
 
 
 def clear_caches():
     _workspace.clear()
+
+
+def _side(device) -> "torch.cuda.Stream":
+    """The engine's side stream on `device` (set_streams(2)): weight gradients run there, next to the data-gradient chain."""
+    device = torch.device(device)
+    st = _side_streams.get(device)
+    if st is None:
+        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 def bump_weight_epoch() -> None:
@@ -253,6 +263,8 @@ def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
     capturing = _capturing()      # under graph capture always re-pack (the packing kernel must be part of the graph)
     ent = None if capturing else cache.get(key)
     if ent is not None and ent[0] == stamp:
+        if ent[3] is not None and ent[3][0] != torch.cuda.current_stream().cuda_stream:
+            torch.cuda.current_stream().wait_event(ent[3][1])     # packed on another stream: order this stream after it
         return ent[1], ent[2]
     Cout, Cin, KH, KW = w.shape
     rows, cols = (Cout_p, Cin_p) if mode == 0 else (Cin_p, Cout_p)
@@ -260,7 +272,12 @@ def _packed(w: torch.Tensor, Cout_p: int, Cin_p: int, mode: int, tag: str = ""):
     lo = torch.empty_like(hi) if _cfg["split"] else None
     _call("fcd_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, Cout_p, Cin_p, mode, hi.data_ptr(), _lib.ptr(lo))
     if not capturing:
-        cache[key] = (stamp, hi, lo)
+        ev = None
+        if _cfg["streams"] > 1:
+            e = torch.cuda.Event()
+            e.record()
+            ev = (torch.cuda.current_stream().cuda_stream, e)
+        cache[key] = (stamp, hi, lo, ev)
     return hi, lo
 
 
@@ -313,10 +330,11 @@ def _w_pack4_out(w: torch.Tensor) -> torch.Tensor:
 def _ws(device, nbytes: int) -> torch.Tensor:
     if _capturing():              # graph-private memory must not leak into the eager cache
         return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
-    cur = _workspace.get(device)
+    key = (torch.device(device), torch.cuda.current_stream(device).cuda_stream)     # one scratch per stream: launches on
+    cur = _workspace.get(key)                                                       # different streams may run concurrently
     if cur is None or cur.numel() < nbytes:
         cur = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspace[device] = cur
+        _workspace[key] = cur
     return cur
 
 
@@ -340,6 +358,8 @@ class Tape:
         self.acts: List[Act] = []
         self.pgrads: Dict[int, torch.Tensor] = {}   # id(param) -> grad (this replay)
         self.params: Dict[int, torch.Tensor] = {}
+        self.forked = False                         # work of this replay is in flight on the side stream
+        self.held: List = []                        # buffers that work reads: kept alive until it has been joined
 
     def push(self, fn):
         if self.record:
@@ -364,13 +384,34 @@ class Tape:
         self.params[k] = p
         return g, 0
 
+    def side_join(self):
+        """Make the current stream wait for the side stream's work of this replay and release the buffers it was reading."""
+        if self.forked:
+            torch.cuda.current_stream().wait_stream(_side(self.device))
+            self.forked = False
+        self.held.clear()
+
+    def on_side(self, fn, *hold):
+        """Run `fn()` on the side stream, ordered after everything issued so far on the current stream.  One piece of side
+        work is in flight at a time (the previous one is joined first), `hold` stays referenced until the next join."""
+        self.side_join()
+        side = _side(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        self.forked = True
+        self.held.extend(hold)
+
     def run(self):
         for a in self.acts:
             a.reset_grad()
         self.pgrads = {}
-        for fn in reversed(self.ops):
-            fn(self)         # the tape is passed in (closures must not capture it: tape <-> closure cycles would
+        try:
+            for fn in reversed(self.ops):
+                fn(self)     # the tape is passed in (closures must not capture it: tape <-> closure cycles would
                              # keep a whole iteration's device buffers alive until Python's cyclic GC runs)
+        finally:
+            self.side_join()
         for a in self.acts:      # gradient buffers are per replay
             a.reset_grad()
         return self.pgrads
@@ -450,18 +491,24 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     def backward(tape):
         dz = z.dz
         assert dz is not None, "conv backward: output gradient missing"
+
+        def wgrad():
+            nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
+            ws = _ws(tape.device, nbytes)
+            _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
+                  N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
+                  tag=f"conv_wgrad_{eng} {shape}", flops=flops)
+
         if not frozen:
             gw, acc = tape.pgrad(w)
             gb = None
             if b is not None and not z.db_done:
                 gb, accb = tape.pgrad(b)
                 assert accb == acc
-            nbytes = _lib.load().fcd_conv2d_wgrad_workspace(N, H, W, Cin_p, Cout_p, KH, KW, stride, pad, _cfg["engine"])
-            ws = _ws(tape.device, nbytes)
-            _call("fcd_conv2d_wgrad", x.p_hi(), x.p_lo(), x.ld, dz.p_hi(), dz.p_lo(), dz.ld, gw.data_ptr(), _lib.ptr(gb),
-                  N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
-                  tag=f"conv_wgrad_{eng} {shape}", flops=flops)
         z.db_done = False
+        side = _cfg["streams"] > 1 and not frozen
+        if not frozen and not side:
+            wgrad()
         if x_needs_grad:
             g = x.grad
             addend = g.data_ptr() if x.ready else None
@@ -477,6 +524,10 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
                       wd_hi.data_ptr(), _lib.ptr(wd_lo), addend, x.ld, g.data_ptr(), x.ld, N, H, W, Cin_p, Cout_p, KH, KW,
                       stride, pad, _cfg["engine"], tag=f"conv_dgrad_{deng} {shape}", flops=flops)
             x.mark_ready()
+        if side:
+            # the weight gradient is off the critical path (nothing in this replay reads it): it runs on the side stream
+            # AFTER the data gradient (both want every SM) and so overlaps the HBM-bound BatchNorm backward of the next layer
+            tape.on_side(wgrad, dz)
         z.dz = None
 
     tape.push(backward)

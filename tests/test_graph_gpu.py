@@ -93,9 +93,17 @@ def _no_leaked_state():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("form", ["whole", "segmented"])
+@pytest.mark.parametrize("form", ["whole", "segmented", "whole-2streams"])
 def test_graph_replay_matches_eager(form):
     fb.set_precision("parity")
+    fb.set_streams(2 if form.endswith("2streams") else 1)      # side-stream weight gradients become parallel graph branches
+    try:
+        _graph_replay_matches_eager(form.split("-")[0])
+    finally:
+        fb.set_streams(1)
+
+
+def _graph_replay_matches_eager(form):
     steps = 3
     eager_losses, want = _eager_run(steps)
     eager_again, _ = _eager_run(steps)

@@ -3,6 +3,8 @@ transposed-convolution), `OutConv`, `ResidualBlock` called on NCHW tensors like 
 parameter gradients and running statistics against the CPU oracle's restatement of the same blocks driven by the module's own
 state_dict.  Also: the supported channel widths are validated in the constructors with a clear error, and packed-weight
 caches follow `.data` writes after `invalidate_weight_cache()`."""
+import re
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -31,13 +33,19 @@ def _randomise(mod, seed):
                 v.copy_(0.3 * torch.randn(v.shape, generator=g) + (1.0 if "weight" in k and v.numel() > 1 else 0.0))
 
 
-def _compare(mod, sd, prefix, out, out_o, ins, ins_o, tol_g=5e-3):
+# conv bias in front of a train-mode BatchNorm: analytically zero gradient (rounding noise on both sides)
+_ZERO_GRAD = re.compile(r".*double_conv\.[03]\.bias|conv[12]\.bias")
+
+
+def _compare(mod, sd, prefix, out, out_o, ins, ins_o, tol_g=5e-3, train=True):
     assert rel_err(out, out_o) < 1e-3, rel_err(out, out_o)
     for a, b in zip(ins, ins_o):
         assert rel_l2(a.grad, b.grad) < tol_g, rel_l2(a.grad, b.grad)
+    gmax = max(float(p.grad.abs().max()) for p in mod.parameters())
     for k, p in mod.named_parameters():
         r = sd[f"{prefix}.{k}" if prefix else k].grad
-        if r.abs().max() < 1e-5:
+        if train and _ZERO_GRAD.fullmatch(k):
+            assert float(p.grad.abs().max()) < 1e-3 * gmax, (k, float(p.grad.abs().max()))
             continue
         assert rel_l2(p.grad, r) < tol_g, (k, rel_l2(p.grad, r))
 
@@ -62,7 +70,7 @@ def test_double_conv_down_residual(train):
         xo = x0.clone().requires_grad_(True)
         out_o = run(sd, xo)
         (out_o * r).sum().backward()
-        _compare(mod, sd, prefix, out, out_o, [x], [xo])
+        _compare(mod, sd, prefix, out, out_o, [x], [xo], train=train)
         if train:
             own = mod.state_dict()
             for k, v in sd.items():

@@ -274,3 +274,41 @@ def test_full_batch_properties():
         moved = netG(x2)
     assert torch.equal(moved[:, :, 64:, 64:], full[:, :, 64:, 64:])
     assert not torch.equal(moved[:, :, :32, :32], full[:, :, :32, :32])
+
+
+@pytest.mark.parametrize("kind,name", [("generator", "g13_train.pt"), ("segmentor", "s4_bilinear_odd.pt"), ("discriminator", "d13.pt")])
+def test_side_stream_weight_gradients_match_the_single_stream_path(kind, name):
+    """set_streams(2) moves every weight-gradient kernel to a side stream (it then overlaps the HBM-bound BatchNorm backward of
+    the next layer): outputs are bit-identical, parameter and input gradients agree to the fp32-atomics level, also when the
+    same tape is replayed twice (retain_graph) and when gradients accumulate over the two siamese branches."""
+    fb.set_precision("parity")
+    f = load_golden(name)
+    C = f["C"]
+    if kind == "generator":
+        make, spec = (lambda: fb.Generator(C)), O.generator_spec(C)
+    elif kind == "segmentor":
+        make, spec = (lambda: fb.Segmentor(C, 1, True)), O.segmentor_spec(C, 1, True)
+    else:
+        make, spec = (lambda: fb.Discriminator_SRGAN_simple(C)), O.discriminator_spec(C)
+    res = {}
+    try:
+        for streams in (1, 2):
+            fb.set_streams(streams)
+            net = _load(make(), spec, f["seed"]).train()
+            x = f["x"].to(DEV).requires_grad_(True)
+            ins = [x] if kind == "generator" else [x, f["y"].to(DEV).requires_grad_(True)]
+            out = net(*ins)
+            loss = (out * f["r"].to(DEV)).sum()
+            loss.backward(retain_graph=True)
+            loss.backward()
+            torch.cuda.synchronize()
+            res[streams] = (out.detach().clone(), [t.grad.clone() for t in ins], {k: p.grad.clone() for k, p in net.named_parameters()})
+    finally:
+        fb.set_streams(1)
+    assert torch.equal(res[1][0], res[2][0])
+    for a, b in zip(res[1][1], res[2][1]):
+        assert rel_err(b, a) < 1e-5
+    for k, a in res[1][2].items():
+        if a.abs().max() < 1e-6:
+            continue
+        assert rel_err(res[2][2][k], a) < 2e-5, k

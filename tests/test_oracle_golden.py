@@ -229,3 +229,28 @@ def test_segmentor_gradient_conditioning():
     c1, g1 = run(1e-5)
     assert rel_err(c1, c0) < 1e-3            # the parity quantity is well conditioned
     assert 1e-3 < rel_l2(g1, g0) < 5e-2      # its gradient is not
+
+
+def test_perception_gradient_conditioning():
+    """Documents why the perception loss's END-TO-END gradients are compared at 2e-2 (L2) / 1e-1 (element-wise) on the GPU
+    (tests/test_perception_gpu.py): in the fp64 oracle itself a 1e-5 relative perturbation of the generated image moves the
+    loss VALUE by < 1e-6 but its gradient by several 1e-3 in relative L2 and > 1e-2 of its maximum."""
+    from tests._util import rel_l2
+    f = load_golden("perception.pt")
+    _, sd = _vgg_sd()
+    sd = {k: v.double() for k, v in sd.items()}
+    d = f["perband"]
+
+    def run(eps):
+        g = d["g"].double().clone()
+        if eps:
+            g = g * (1 + eps * torch.randn(g.shape, generator=torch.Generator().manual_seed(0)).double())
+        g.requires_grad_(True)
+        v = O.perception_loss(sd, d["t"].double(), g, d["cmap"].double(), 1, True)
+        v.backward()
+        return v.item(), g.grad
+
+    v0, g0 = run(0.0)
+    v1, g1 = run(1e-5)
+    assert abs(v1 - v0) < 1e-5 * abs(v0)
+    assert 1e-3 < rel_l2(g1, g0) < 2e-2 and rel_err(g1, g0) > 5e-3

@@ -3,9 +3,12 @@ golden vectors recorded from the UNMODIFIED reference's PerceptionLoss / CNetLos
 torchvision's VGG16 initialised under a fixed seed (oracle/make_golden_perception.py; the ImageNet weights of Loss.py:25
 cannot be downloaded here, and a seeded random VGG16 pins the arithmetic just as well).
 
-Tolerance: 1e-3 relative on the loss values (16 convolution layers deep, parity precision = split-bf16 operands); gradients
-1e-3 of the tensor maximum in relative L2 / 1e-2 element-wise: ReLU / max-pool kinks inside a 13-layer stack flip isolated
-elements (tests/_util.check_grad_summary_l2 explains the effect)."""
+Tolerance: 1e-3 relative on the loss values (13 convolution layers deep, parity precision = split-bf16 operands; measured
+< 1e-4).  Gradients: 2e-2 in relative L2, 1e-1 of the tensor maximum element-wise — the conditioning of the function, not of
+the kernels: in the fp64 oracle itself a 1e-5 relative perturbation of the generated image (the size of the CUDA path's forward
+error) moves d loss / d image by 5.3e-3 in relative L2 and 3.3e-2 of its maximum (13 ReLU layers + 4 max-pools: every kink
+crossed flips a whole receptive field's worth of gradient; tests/test_oracle_golden.py::test_perception_gradient_conditioning,
+profiles/r02_gradient_conditioning.log).  Measured here: 2e-3 ... 8e-3 in L2, 1e-2 ... 4e-2 element-wise."""
 import pytest
 import torch
 
@@ -15,7 +18,7 @@ from tests._util import load_golden, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-VTOL, G_L2, G_MAX = 1e-3, 2e-3, 2e-2
+VTOL, G_L2, G_MAX = 1e-3, 2e-2, 1e-1
 
 
 @pytest.fixture(scope="module")
