@@ -321,7 +321,8 @@ def run_ours(args):
 
     # the very first iteration from the initial weights, eagerly: its losses are what the CPU leg (unmodified reference, same
     # seeds, same batch) must reproduce — checked below when the CPU sample runs the full batch
-    first_losses = [float(v) for v in eager_step(*data)]
+    first_losses = [float(v.detach()) for v in eager_step(*data)]
+    torch.cuda.empty_cache()        # the eager iteration's blocks must not sit beside the graph's private pool (config 3 is memory-bound)
 
     step = eager_step
     gstep = None
@@ -437,6 +438,10 @@ def run_ours(args):
 
     # ---- instrumented pass: per-call CUDA events -> dominant kernel roofline (not part of the timed numbers).
     # Every rank runs it (the step contains collectives when world > 1); only rank 0 records events.
+    gstep = None                  # release the graphs' private pool first: the eager pass needs a whole iteration's memory again
+    step = eager_step
+    del staging
+    torch.cuda.empty_cache()
     nprof = min(args.steps, 3)
     fb.set_streams(1)             # one stream, so that the events bracket each kernel alone
     if rank == 0:
@@ -480,7 +485,6 @@ def run_ours(args):
                 "step_algorithmic_tflops": round(cfg["gf"] * 1e9 * world * B * args.steps / (ms_total * 1e-3) / 1e12, 1),
                 "step_frac_of_peak": round(cfg["gf"] * 1e9 * B * args.steps / (ms_total * 1e-3) / 1e12 / pk["tflops_sustained"], 4),
                 "top5": [{"kernel": k, "ms_per_step": round(v[0] / nprof, 3), "launches": v[1] // nprof} for k, v in top[:5]]}
-        gstep = None              # release the graphs' memory pool before the baselines run
         gpu_base = cpu = None
         loss_check = None
         if world == 1 and not args.no_gpu_baseline:

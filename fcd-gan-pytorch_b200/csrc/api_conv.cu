@@ -16,14 +16,21 @@ void set_error(int code, const char* fmt, ...) {
     va_end(ap);
 }
 
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < FCD_MAX_DEVICES) ? dev : 0;
+}
+
+// per device: a process may drive several GPUs (the reference pins one script per GPU, SURVEY.md §2.1, but nothing here
+// relies on it)
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[FCD_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 // implemented in conv_tc.cu / conv_simt.cu / wgrad_tc.cu

@@ -785,11 +785,11 @@ constexpr int HALO_SMEM_MAX = 227 * 1024 - 1024;   // opt-in limit minus the ker
 template <int BLOCK_N, bool SPLIT>
 static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
                             const CUtensorMap& mz, const ConvHaloParams& hp, int smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once()) {
         FCD_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HALO_SMEM_MAX));
-        attr_set = true;
+        attr_once() = true;
     }
     long long grid = sm_count() / hp.c.n_blocks * hp.c.n_blocks;
     if (grid < hp.c.n_blocks) grid = hp.c.n_blocks;
@@ -844,11 +844,11 @@ template <int BLOCK_N, bool SPLIT>
 static int launch_conv_tc(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh,
                           const CUtensorMap& mwl, const ConvTcParams& p, cudaStream_t stream) {
     using C = Cfg<BLOCK_N, SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once()) {
         FCD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
-        attr_set = true;
+        attr_once() = true;
     }
     long long grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
     conv_tc_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, p);

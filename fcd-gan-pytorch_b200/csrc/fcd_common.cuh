@@ -44,7 +44,15 @@ void set_error(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();
+constexpr int FCD_MAX_DEVICES = 64;
+int current_device();     // cudaGetDevice, clamped to [0, FCD_MAX_DEVICES)
+int sm_count();           // of the current device
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: remember it per device ordinal
+struct PerDeviceOnce {
+    bool done[FCD_MAX_DEVICES] = {};
+    bool& operator()() { return done[current_device()]; }
+};
 
 // ---- split-bf16 helpers --------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

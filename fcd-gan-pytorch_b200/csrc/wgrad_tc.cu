@@ -315,11 +315,11 @@ template <int BLOCK_N, bool SPLIT>
 static int launch_wgrad(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mgh, const CUtensorMap& mgl,
                         const WgradParams& p, cudaStream_t stream) {
     using C = WCfg<BLOCK_N, SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once()) {
         FCD_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
-        attr_set = true;
+        attr_once() = true;
     }
     const unsigned grid = static_cast<unsigned>(p.m_blocks) * p.n_blocks * p.ksplit;
     wgrad_tc_kernel<BLOCK_N, SPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(mxh, mxl, mgh, mgl, p);
@@ -561,11 +561,11 @@ static bool wgrad_halo_fits(int n_r, int n_s, int s_step, bool split, WHaloParam
 template <bool SPLIT>
 static int launch_wgrad_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mgh, const CUtensorMap& mgl,
                              const WHaloParams& p, unsigned grid, cudaStream_t stream) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
     const int smem_bytes = H_SMEM_BUDGET + 1024 + 256;
-    if (!attr_set) {
+    if (!attr_once()) {
         FCD_CUDA_OK(cudaFuncSetAttribute(wgrad_halo_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_set = true;
+        attr_once() = true;
     }
     wgrad_halo_kernel<SPLIT><<<grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mgh, mgl, p);
     FCD_LAUNCH_OK();

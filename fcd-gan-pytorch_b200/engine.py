@@ -76,7 +76,8 @@ PROFILE = None       # set to a list: every C-ABI call is bracketed by CUDA even
 
 
 def _raw_stream() -> int:
-    """cudaStream_t of torch's current stream on the current device (the capture stream under CUDA-graph capture)."""
+    """cudaStream_t of torch's current stream on the current device (the capture stream under CUDA-graph capture).  The
+    networks make their tensors' device current for the duration of a pass (NetFunction), so this is the tensors' device."""
     return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
@@ -1033,7 +1034,8 @@ class NetFunction(torch.autograd.Function):
                 raise _lib.FcdError("fcdgan_b200 networks take fp32 CUDA tensors (there is no CPU path)")
         record = any(ctx.needs_input_grad[2:])
         tape = Tape(inputs[0].device, record)
-        outs, slot, input_acts = runner.fn(tape, inputs, ctx.needs_input_grad[2:2 + n_inputs])
+        with torch.cuda.device(inputs[0].device):       # kernels launch on the TENSORS' device, whatever device is current
+            outs, slot, input_acts = runner.fn(tape, inputs, ctx.needs_input_grad[2:2 + n_inputs])
         ctx.tape, ctx.slot, ctx.input_acts = tape, slot, input_acts
         ctx.n_inputs = n_inputs
         ctx.param_ids = [id(p) for p in runner.params]
@@ -1055,7 +1057,8 @@ class NetFunction(torch.autograd.Function):
 
         tape.ops.insert(0, grab)
         try:
-            pg = tape.run()
+            with torch.cuda.device(tape.device):
+                pg = tape.run()
         finally:
             tape.ops.pop(0)
             ctx.slot["dout"] = None

@@ -33,6 +33,7 @@ class GraphedStep:
                 fn(*self.static_inputs)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()        # the warm-up's blocks sit in the side stream's pool: hand them back before the capture
         self.graph = torch.cuda.CUDAGraph()
         n0 = E.launch_count
         # "thread_local" lets other threads (e.g. the NCCL watchdog) keep making CUDA calls during the capture
@@ -74,6 +75,7 @@ class SegmentedStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         self.graphs, self.outputs = [], []
         n0 = E.launch_count
         pool = None
@@ -135,6 +137,7 @@ class YieldingStep:
                 drive(genfn(*self.static_inputs), sync.on_grads)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         self.graphs, self.actions = [], []
         n0 = E.launch_count
         gen = genfn(*self.static_inputs)
