@@ -179,7 +179,7 @@ def _loss_list(out):
 
 # ------------------------------------------------------------------------------------------------
 def build_ours(config, dev, B, capturable):
-    """-> (genfn(*data) -> step generator yielding (network, wait) at its exchange points, trained networks)."""
+    """-> (genfn(*data) -> step generator yielding (network, wait) at its exchange points, trained networks, all networks)."""
     import torch
 
     import fcdgan_b200 as fb
@@ -226,17 +226,17 @@ def build_ours(config, dev, B, capturable):
             optD.step()
             return gen_loss, d_loss
 
-        return genfn, [n for n in (netG, netD) if n is not None]
+        return genfn, [n for n in (netG, netD) if n is not None], list(nets.values())
     if config == "3":
         optG, optS = adam(netG), adam(netS)
         crit = fb.CNetLoss(channel=Cc)
-        return (lambda x, y: S.usss_gen(netG, netS, x, y, crit, optG, optS, ssim_weight=0.3)), [netG, netS]
+        return (lambda x, y: S.usss_gen(netG, netS, x, y, crit, optG, optS, ssim_weight=0.3)), [netG, netS], list(nets.values())
     gcrit = fb.CGeneratorLoss(channel=Cc, perception_perBand=(config == "4"))
     netG.eval()                                                                   # Demo_RSSS.py:240, Demo_WSSS.py:207
     optS, optD = rms(netS), rms(netD)
     if config == "4":
-        return (lambda x, y, region: S.rsss_gen(netG, netS, netD, x, y, region, gcrit, optS, optD)), [netS, netD]
-    return (lambda x, y, x_nc, y_nc: S.wsss_gen(netG, netS, netD, x, y, x_nc, y_nc, gcrit, optS, optD)), [netS, netD]
+        return (lambda x, y, region: S.rsss_gen(netG, netS, netD, x, y, region, gcrit, optS, optD)), [netS, netD], list(nets.values())
+    return (lambda x, y, x_nc, y_nc: S.wsss_gen(netG, netS, netD, x, y, x_nc, y_nc, gcrit, optS, optD)), [netS, netD], list(nets.values())
 
 
 def build_reference(config, dev, B, staged=True):
@@ -304,9 +304,9 @@ def run_ours(args):
     fb.set_precision(args.precision)
     fb.set_streams(args.streams)
     B = args.batch or cfg["B"]
-    use_graph = args.graph in ("on", "auto")
+    use_graph = args.graph in ("on", "auto", "segmented")
 
-    genfn, nets = build_ours(args.config, dev, B, use_graph)
+    genfn, nets, all_nets = build_ours(args.config, dev, B, use_graph)
     P.broadcast_parameters(nets)
     sync = P.GradSync()
     data = synth_for(args.config, B, 1234 + rank, device=dev)
@@ -329,19 +329,19 @@ def run_ours(args):
     graph_note = "eager"
     if use_graph:
         try:
-            if world == 1:
+            if world == 1 and args.graph != "segmented":
                 from fcdgan_b200.graph import GraphedStep
-                gstep = GraphedStep(lambda *a: _loss_list(drive(genfn(*a))), data, warmup=3)
+                gstep = GraphedStep(lambda *a: _loss_list(drive(genfn(*a))), data, warmup=3, modules=all_nets)
                 graph_note = "whole iteration captured in one CUDA graph (fcdgan_b200.graph.GraphedStep)"
-            elif args.collectives == "captured":
+            elif args.collectives == "captured" and world > 1:
                 # experiment: the NCCL all-reduces captured INSIDE the one graph (round 1: hung on this stack)
                 from fcdgan_b200.graph import GraphedStep
                 gstep = GraphedStep(lambda *a: _loss_list(drive(genfn(*a), sync.on_grads)), data, warmup=3,
-                                    capture_error_mode="thread_local")
+                                    capture_error_mode="thread_local", modules=all_nets)
                 graph_note = "whole iteration INCLUDING the NCCL all-reduces captured in one CUDA graph"
             else:
                 from fcdgan_b200.graph import YieldingStep
-                gstep = YieldingStep(genfn, sync, data, warmup=3)
+                gstep = YieldingStep(genfn, sync, data, warmup=3, modules=all_nets)
                 graph_note = (f"{len(gstep.graphs)} CUDA graphs cut at the step's gradient-exchange points, NCCL all-reduces issued "
                               "eagerly between them (fcdgan_b200.graph.YieldingStep)")
 
@@ -677,7 +677,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's)")
     ap.add_argument("--precision", choices=["parity", "fast"], default="parity")
     ap.add_argument("--impl", choices=["ours", "reference", "cudnn"], default="ours")
-    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto", help="capture the iteration in a CUDA graph")
+    ap.add_argument("--graph", choices=["auto", "on", "off", "segmented"], default="auto",
+                    help="capture the iteration in a CUDA graph (segmented: the N > 1 form — graphs cut at the exchange points — also at N = 1)")
     ap.add_argument("--collectives", choices=["eager", "captured"], default="eager",
                     help="N > 1: NCCL calls issued eagerly between CUDA graphs (default) or captured inside one graph (experiment)")
     ap.add_argument("--streams", type=int, default=1, help="engine streams (independent branches / weight gradients run concurrently)")

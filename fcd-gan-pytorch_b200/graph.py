@@ -11,9 +11,18 @@ graph-private pool) into one CUDA graph removes that bound: a replay is a single
 
 Requirements (the usual CUDA-graph rules): shapes fixed; optimizers constructed with `capturable=True`;
 `zero_grad(set_to_none=True)` inside `fn`; no host synchronisation inside `fn`.
+
+`modules=` — every network the step touches.  Their `.grad` tensors are dropped after the warm-up, BEFORE the capture: a
+gradient tensor left over from the warm-up lives in the ordinary allocator pool, and a step that accumulates into it before
+zeroing it (the wasted Segmentor gradients of `d_loss.backward()` in Demo_RSSS.py:305, the first of the two backward sweeps of
+Demo_USSS.py:327) would bake its address into the graph and then free it — every replay would write through a dangling
+pointer (found in round 2: replays of the RSSS / USSS / WSSS steps faulted as soon as the allocator returned that block to the
+driver).  With the gradients dropped, the capture allocates them from the graph's private pool, where the address stays valid.
 """
 from __future__ import annotations
 
+import gc
+import os
 from typing import Callable, Sequence
 
 import torch
@@ -21,9 +30,15 @@ import torch
 from . import engine as E
 
 
+def _drop_grads(modules) -> None:
+    for m in modules:
+        for p in m.parameters():
+            p.grad = None
+
+
 class GraphedStep:
     def __init__(self, fn: Callable, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 capture_error_mode: str = "global"):
+                 capture_error_mode: str = "global", modules: Sequence[torch.nn.Module] = ()):
         self.fn = fn
         self.static_inputs = list(static_inputs)
         side = torch.cuda.Stream()
@@ -33,7 +48,9 @@ class GraphedStep:
                 fn(*self.static_inputs)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        _drop_grads(modules)
         torch.cuda.empty_cache()        # the warm-up's blocks sit in the side stream's pool: hand them back before the capture
+        gc.collect()                    # see YieldingStep: no autograd node of an earlier iteration may survive into the capture
         self.graph = torch.cuda.CUDAGraph()
         n0 = E.launch_count
         # "thread_local" lets other threads (e.g. the NCCL watchdog) keep making CUDA calls during the capture
@@ -125,7 +142,7 @@ class YieldingStep:
     """
 
     def __init__(self, genfn: Callable, sync, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 capture_error_mode: str = "thread_local"):
+                 capture_error_mode: str = "thread_local", modules: Sequence[torch.nn.Module] = ()):
         from .steps import drive
 
         self.sync = sync
@@ -137,23 +154,36 @@ class YieldingStep:
                 drive(genfn(*self.static_inputs), sync.on_grads)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        _drop_grads(modules)            # see the module docstring: no warm-up gradient tensor may be written by the graphs
         torch.cuda.empty_cache()
         self.graphs, self.actions = [], []
         n0 = E.launch_count
         gen = genfn(*self.static_inputs)
         pool, unpack_next, done = None, False, False
         while not done:
+            # autograd nodes of earlier (eager / warm-up) iterations that are still alive would be re-used by this capture with
+            # the stream they were created on; a dead reference cycle is enough to keep them: collect before every capture
+            gc.collect()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, capture_error_mode=capture_error_mode):
-                if unpack_next:
-                    sync.unpack()
-                    unpack_next = False
-                try:
-                    net, wait = next(gen)
-                    sync.pack(net)
-                except StopIteration as e:
-                    self.outputs = e.value
-                    done = True
+            err = None
+            try:
+                with torch.cuda.graph(g, pool=pool, capture_error_mode=capture_error_mode):
+                    try:
+                        if unpack_next:
+                            sync.unpack()
+                            unpack_next = False
+                        try:
+                            net, wait = next(gen)
+                            sync.pack(net)
+                        except StopIteration as e:
+                            self.outputs = e.value
+                            done = True
+                    except BaseException as e:      # keep the ROOT cause: capture_end() would mask it with "invalidated"
+                        err = e
+            except BaseException as e:
+                err = err or e
+            if err is not None:
+                raise RuntimeError(f"YieldingStep: capture of graph {len(self.graphs)} failed: {type(err).__name__}: {err}") from err
             pool = g.pool()
             self.graphs.append(g)
             if not done:                    # keeps the backend's call sequence identical on every rank during set-up
@@ -171,8 +201,14 @@ class YieldingStep:
             dst.copy_(src, non_blocking=True)
 
     def __call__(self):
+        debug = bool(os.environ.get("FCD_GRAPH_DEBUG"))
         for i, g in enumerate(self.graphs):
             g.replay()
+            if debug:                       # localise a faulting segment (FCD_GRAPH_DEBUG=1)
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise RuntimeError(f"YieldingStep: replay of graph {i} of {len(self.graphs)} faulted: {e}") from e
             if i < len(self.actions):
                 net, wait = self.actions[i]
                 self.sync.launch(net)

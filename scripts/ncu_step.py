@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 fb.set_precision(sys.argv[2] if len(sys.argv) > 2 else "parity")
 fb.set_streams(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 B = bench.CONFIGS[config]["B"]
-genfn, nets = bench.build_ours(config, dev, B, False)
+genfn, nets, _ = bench.build_ours(config, dev, B, False)
 data = bench.synth_for(config, B, 1234, device=dev)
 for _ in range(3):
     drive(genfn(*data))

@@ -160,3 +160,69 @@ def _graph_replay_matches_eager(form):
         if ref.numel() >= 4096:
             off = (diff > 1e-6 + 1e-4 * ref.abs()).float().mean().item()
             assert off < 2e-2, f"{k}: {off:.2%} of the elements differ"
+
+
+@pytest.mark.parametrize("form", ["whole", "segmented"])
+def test_rsss_step_graph_forms_match_eager(form):
+    """The RSSS iteration accumulates into the Segmentor's gradients (`d_loss.backward()`, Demo_RSSS.py:305) BEFORE it zeroes
+    them (Demo_RSSS.py:330) and has an optimizer step in its middle: gradient tensors left over from the warm-up must not be
+    baked into the graphs (graph.py docstring), autograd state crosses the graph boundaries of the segmented form, and the
+    replays must give the eager loss trajectory.  `empty_cache()` after the capture returns every free block of the ordinary
+    pool to the driver, so a dangling pointer inside a graph faults instead of silently scribbling."""
+    from fcdgan_b200 import steps as S
+    fb.set_precision("parity")
+    C_, B_, H_, W_ = 4, 2, 48, 40
+
+    def setup():
+        nets = []
+        for make, spec, seed in ((lambda: fb.Generator(C_), O.generator_spec(C_), 11), (lambda: fb.Segmentor(C_, 1, True), O.segmentor_spec(C_, 1, True), 12),
+                                 (lambda: fb.Discriminator_SRGAN_simple(C_), O.discriminator_spec(C_), 13)):
+            n = make(); n.load_state_dict(O.make_state_dict(spec, seed)); nets.append(n.to(DEV).train())
+        netG, netS, netD = nets
+        netG.eval()
+        optS = torch.optim.RMSprop(netS.parameters(), lr=5e-5, capturable=True)
+        optD = torch.optim.RMSprop(netD.parameters(), lr=5e-5, capturable=True)
+        g = torch.Generator().manual_seed(6)
+        x = torch.randn(B_, C_, H_, W_, generator=g).to(DEV)
+        y = (x.cpu() + 0.3 * torch.randn(B_, C_, H_, W_, generator=g)).to(DEV)
+        region = (torch.rand(B_, 1, H_, W_, generator=g) > 0.5).float().to(DEV)
+        crit = fb.CGeneratorLoss(channel=C_)
+        # g_weight = 0: tiles this small are below MS-SSIM's 160-pixel minimum (ssim.py:194-197); the generator term is covered by
+        # tests/test_steps_gpu.py
+        gen = lambda x, y, region: S.rsss_gen(netG, netS, netD, x, y, region, crit, optS, optD, g_weight=0.0)
+        return (netG, netS, netD), (optS, optD), gen, [x, y, region]
+
+    def pick(out):
+        return out["d_loss"].item(), out["s_loss"].item()
+
+    steps = 3
+    nets, opts, gen, data = setup()
+    eager = [pick(S.drive(gen(*data))) for _ in range(steps)]
+    nets, opts, gen, data = setup()
+    again = [pick(S.drive(gen(*data))) for _ in range(steps)]
+    spread = max(abs(a - b) / max(1.0, abs(a)) for la, lb in zip(eager, again) for a, b in zip(la, lb))
+    nets, opts, gen, data = setup()
+    state = [copy.deepcopy(n.state_dict()) for n in nets]
+    if form == "whole":
+        step = GraphedStep(lambda *a: S.drive(gen(*a)), data, warmup=2, modules=nets)
+    else:
+        step = YieldingStep(gen, GradSync(), data, warmup=2, modules=nets)
+        assert len(step.graphs) == 3
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        for net, sd in zip(nets, state):
+            own = net.state_dict()
+            for k, v in sd.items():
+                own[k].copy_(v)
+        for opt in opts:
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+    junk = torch.full((64 << 20,), float("nan"), device=DEV)     # whatever the allocator hands out next must not alias graph memory
+    for i in range(steps):
+        got = pick(step())
+        t = 1e-6 if i == 0 else max(3e-5, 4 * spread)
+        for a, b in zip(got, eager[i]):
+            assert abs(a - b) <= t * max(1.0, abs(b)), (form, i, got, eager[i], spread)
+    assert torch.isnan(junk).all()
