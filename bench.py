@@ -9,7 +9,7 @@
              y_fake = G(x); masked L1(y, y_fake, cmap = 0) -> backward                                    (Demo_USSS.py:142-159)
              c_out = D(x*(1-cmap), y*(1-cmap)); nc_out = D(x*(1-cmap), (y*(1-r)+x*r)*(1-cmap)); d_loss     (Demo_RSSS.py:285-307)
     g32  north-star configuration: Generator forward + backward + Adam, 32 tiles of 13x256x256, 203.6 GF/tile
-    3    USSS joint iteration G + S + CNetLoss with a live MS-SSIM gradient, 13x512x512 (Demo_USSS.py:305-341), 3961 GF/pair
+    3    USSS joint iteration G + S + CNetLoss with a live MS-SSIM gradient, 32 pairs of 13x512x512 (Demo_USSS.py:305-341), 3961 GF/pair
     4    RSSS adversarial iteration G + S + D, 16 pairs of 13x256x256 per GPU (Demo_RSSS.py:270-332), 889 GF/pair
     5    WSSS adversarial iteration, 32 (changed, unchanged) items of 3x256x256 per GPU (Demo_WSSS.py:240-323), 1654 GF/item
 One "step" = one whole iteration, optimizer steps included.  N > 1 (torchrun): every rank runs its own batch (weak scaling)
@@ -42,10 +42,10 @@ CONFIGS = {
               workload="configs[1]: Generator+Discriminator fwd/bwd (+Adam/RMSprop step), batch {B}/GPU of 256x256x13 synthetic tile pairs"),
     "g32": dict(metric="tiles_per_sec_generator_fwd_bwd_256x256x13", unit="tiles/s", C=13, H=256, W=256, B=32, gf=203.6, cpu_B=8,
                 nets="G", workload="north star: Generator fwd+bwd (+Adam step), batch {B}/GPU of 13x256x256 synthetic tiles"),
-    "3": dict(metric="tile_pairs_per_sec_usss_joint_step_512x512x13", unit="tile-pairs/s", C=13, H=512, W=512, B=8, gf=3961.0, cpu_B=1,
+    "3": dict(metric="tile_pairs_per_sec_usss_joint_step_512x512x13", unit="tile-pairs/s", C=13, H=512, W=512, B=32, gf=3961.0, cpu_B=1,
               nets="GS",
               workload="configs[2]: USSS joint iteration G+S+CNetLoss (MS-SSIM weight 0.3, perception 0; USSS has no D, SURVEY.md 8(d)), "
-                       "batch {B}/GPU of 512x512x13 synthetic tile pairs (BASELINE names batch 32: does not fit 180 GB, DESIGN.md)"),
+                       "batch {B}/GPU of 512x512x13 synthetic tile pairs (146 GiB of the 178 GiB at batch 32)"),
     "4": dict(metric="tile_pairs_per_sec_rsss_step_256x256x13", unit="tile-pairs/s", C=13, H=256, W=256, B=16, gf=889.0, cpu_B=2,
               nets="GSD", workload="configs[3]: RSSS adversarial iteration G+S+D, batch {B}/GPU of 256x256x13 synthetic OSCD-shape pairs"),
     "5": dict(metric="items_per_sec_wsss_step_256x256x3", unit="items/s", C=3, H=256, W=256, B=32, gf=1654.0, cpu_B=2, nets="GSD",
@@ -488,11 +488,20 @@ def run_ours(args):
         gpu_base = cpu = None
         loss_check = None
         if world == 1 and not args.no_gpu_baseline:
-            try:
-                torch.cuda.empty_cache()
-                gpu_base = gpu_baseline(args.config, B, dev)
-            except Exception as e:
-                gpu_base = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+            Bg = B
+            while True:      # the reference's autograd keeps far more per sample than our tape: halve its batch until it fits
+                try:
+                    torch.cuda.empty_cache()
+                    gpu_base = gpu_baseline(args.config, Bg, dev)
+                    break
+                except torch.OutOfMemoryError:
+                    if Bg == 1:
+                        gpu_base = {"unavailable": "out of memory at batch 1"}
+                        break
+                    Bg //= 2
+                except Exception as e:
+                    gpu_base = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+                    break
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args.config)
             if cpu.get("first_losses") and cpu.get("batch") == B:
