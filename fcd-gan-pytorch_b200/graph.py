@@ -18,6 +18,11 @@ zeroing it (the wasted Segmentor gradients of `d_loss.backward()` in Demo_RSSS.p
 Demo_USSS.py:327) would bake its address into the graph and then free it — every replay would write through a dangling
 pointer (found in round 2: replays of the RSSS / USSS / WSSS steps faulted as soon as the allocator returned that block to the
 driver).  With the gradients dropped, the capture allocates them from the graph's private pool, where the address stays valid.
+
+Do not keep autograd-connected tensors of EARLIER iterations (a loss, a change-density map) alive across the capture: they pin
+that iteration's autograd graph, whose AccumulateGrad nodes — created on the stream that iteration ran on — PyTorch then
+re-uses inside the capture, and the cross-stream wait it inserts ("legacy stream depends on a capturing stream") invalidates
+the capture.  Keep `loss.detach()` / `loss.item()` instead.
 """
 from __future__ import annotations
 

@@ -73,16 +73,18 @@ def main():
     xs, ys, cs = (t[sl].to(dev) for t in (x, y, cmap))
     # 1-rank full batch (every rank computes it for itself; no communication)
     netG, netD = make_nets(dev)
-    gl_full, dl_full = drive(make_gen(netG, netD)(x.to(dev), y.to(dev), cmap.to(dev)))
+    # (losses are detached at once: a live loss keeps its iteration's autograd graph — and with it the AccumulateGrad nodes
+    # created on THIS stream — alive, and a later CUDA-graph capture would re-use those nodes across streams; graph.py docstring)
+    gl_full, dl_full = (v.detach() for v in drive(make_gen(netG, netD)(x.to(dev), y.to(dev), cmap.to(dev))))
     want = grads(netG, netD)
     # N-rank sharded, eager exchange
     netG, netD = make_nets(dev)
     P.broadcast_parameters([netG, netD])
     sync = P.GradSync()
-    gl, dl = drive(make_gen(netG, netD)(xs, ys, cs), sync.on_grads)
+    gl, dl = (v.detach() for v in drive(make_gen(netG, netD)(xs, ys, cs), sync.on_grads))
     got_eager = grads(netG, netD)
     # N-rank sharded, CUDA graphs cut at the exchange points
-    step = YieldingStep(make_gen(netG, netD), sync, [xs, ys, cs], warmup=2)
+    step = YieldingStep(make_gen(netG, netD), sync, [xs, ys, cs], warmup=2, modules=[netG, netD])
     assert len(step.graphs) == 3
     step()
     torch.cuda.synchronize()
@@ -96,7 +98,7 @@ def main():
             err = (a - b).abs().max().item() / scale
             worst = max(worst, err)
             assert err < 2e-5, f"rank {rank} [{what}] {k}: {err:.3g}"
-    losses = torch.stack([gl.detach(), dl.detach()])
+    losses = torch.stack([gl, dl])
     dist.all_reduce(losses)
     losses /= world
     assert abs(losses[0].item() - gl_full.item()) < 1e-6 * max(1, abs(gl_full.item())), (losses, gl_full)

@@ -18,4 +18,9 @@ def test_sharded_step_equals_full_batch_step():
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_dp_equiv.py")],
                          capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
+    if res.returncode != 0 or "DP_EQUIV_OK" not in res.stdout:           # keep the whole transcript where gpurun brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "dp_equiv_failure.log"), "w") as fh:
+            fh.write(res.stdout + "\n---- stderr ----\n" + res.stderr)
     assert res.returncode == 0 and "DP_EQUIV_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])
+    print(res.stdout.strip().splitlines()[-1])
