@@ -90,14 +90,16 @@ def main():
     torch.cuda.synchronize()
     got_graph = grads(netG, netD)
     worst = 0.0
+    # scale of a tensor's error: its own maximum, but not less than 1 % of the largest gradient entry of the run — the last
+    # layer's bias gradient is a 1-element sum of sigmoid'(nc) - sigmoid'(c) terms that nearly cancel (nc_out is D(x, x): its
+    # feature difference is exactly 0), so its own magnitude says nothing about the accuracy of the sums behind it
+    gmax = max(b.abs().max().item() for _, b in want)
     for what, got in (("eager", got_eager), ("graphs", got_graph)):
         for (k, a), (_, b) in zip(got, want):
-            scale = b.abs().max().item()
-            if scale < 1e-7:
-                continue
+            scale = max(b.abs().max().item(), 1e-2 * gmax)
             err = (a - b).abs().max().item() / scale
             worst = max(worst, err)
-            assert err < 2e-5, f"rank {rank} [{what}] {k}: {err:.3g}"
+            assert err < 2e-5, f"rank {rank} [{what}] {k}: {err:.3g} (|ref|max {b.abs().max().item():.3g}, run max {gmax:.3g})"
     losses = torch.stack([gl, dl])
     dist.all_reduce(losses)
     losses /= world
