@@ -12,6 +12,8 @@
     3    USSS joint iteration G + S + CNetLoss with a live MS-SSIM gradient, 32 pairs of 13x512x512 (Demo_USSS.py:305-341), 3961 GF/pair
     4    RSSS adversarial iteration G + S + D, 16 pairs of 13x256x256 per GPU (Demo_RSSS.py:270-332), 889 GF/pair
     5    WSSS adversarial iteration, 32 (changed, unchanged) items of 3x256x256 per GPU (Demo_WSSS.py:240-323), 1654 GF/item
+Configs 3 / 4 / 5 run the step bodies of fcdgan_b200.steps in their `lean` form by default (`--form faithful` replays the reference's
+call sequence including the backward sweeps whose results it discards; same losses, same gradients at every optimizer step).
 One "step" = one whole iteration, optimizer steps included.  N > 1 (torchrun): every rank runs its own batch (weak scaling)
 and the gradients of every trained network are all-reduced over NCCL (fcdgan_b200.parallel.GradSync) at the step body's
 exchange points (fcdgan_b200.steps / graph.YieldingStep).
@@ -178,7 +180,7 @@ def _loss_list(out):
 
 
 # ------------------------------------------------------------------------------------------------
-def build_ours(config, dev, B, capturable):
+def build_ours(config, dev, B, capturable, lean=True):
     """-> (genfn(*data) -> step generator yielding (network, wait) at its exchange points, trained networks, all networks)."""
     import torch
 
@@ -230,13 +232,13 @@ def build_ours(config, dev, B, capturable):
     if config == "3":
         optG, optS = adam(netG), adam(netS)
         crit = fb.CNetLoss(channel=Cc)
-        return (lambda x, y: S.usss_gen(netG, netS, x, y, crit, optG, optS, ssim_weight=0.3)), [netG, netS], list(nets.values())
+        return (lambda x, y: S.usss_gen(netG, netS, x, y, crit, optG, optS, ssim_weight=0.3, lean=lean)), [netG, netS], list(nets.values())
     gcrit = fb.CGeneratorLoss(channel=Cc, perception_perBand=(config == "4"))
     netG.eval()                                                                   # Demo_RSSS.py:240, Demo_WSSS.py:207
     optS, optD = rms(netS), rms(netD)
     if config == "4":
-        return (lambda x, y, region: S.rsss_gen(netG, netS, netD, x, y, region, gcrit, optS, optD)), [netS, netD], list(nets.values())
-    return (lambda x, y, x_nc, y_nc: S.wsss_gen(netG, netS, netD, x, y, x_nc, y_nc, gcrit, optS, optD)), [netS, netD], list(nets.values())
+        return (lambda x, y, region: S.rsss_gen(netG, netS, netD, x, y, region, gcrit, optS, optD, lean=lean)), [netS, netD], list(nets.values())
+    return (lambda x, y, x_nc, y_nc: S.wsss_gen(netG, netS, netD, x, y, x_nc, y_nc, gcrit, optS, optD, lean=lean)), [netS, netD], list(nets.values())
 
 
 def build_reference(config, dev, B, staged=True):
@@ -306,7 +308,7 @@ def run_ours(args):
     B = args.batch or cfg["B"]
     use_graph = args.graph in ("on", "auto", "segmented")
 
-    genfn, nets, all_nets = build_ours(args.config, dev, B, use_graph)
+    genfn, nets, all_nets = build_ours(args.config, dev, B, use_graph, lean=(args.form == "lean"))
     P.broadcast_parameters(nets)
     sync = P.GradSync()
     data = synth_for(args.config, B, 1234 + rank, device=dev)
@@ -518,6 +520,11 @@ def run_ours(args):
                "data": "synthetic",
                "config": {"workload": cfg["workload"].format(B=B), "precision": args.precision, "batch_per_gpu": B,
                           "parallelism": f"dp{world}", "launch": graph_note, "streams": args.streams,
+                          "step_form": (None if args.config in ("2", "g32") else
+                                        "lean: the backward sweeps whose results the reference's loop body discards are skipped (identical "
+                                        "losses / map / gradients at every optimizer step: tests/test_steps_gpu.py::test_lean_steps_*; the "
+                                        "algorithmic minimum SURVEY.md 8(d) counts)" if args.form == "lean" else
+                                        "faithful: the reference's call sequence, call for call (its dead backward sweeps included)"),
                           "l2": "per-step working set (>20 GB) >> 126 MB L2; no flush needed",
                           "algorithmic_gflop_per_unit": cfg["gf"], "peak_mem_GiB": round(peak_mem, 1)},
                "clocks": clocks,
@@ -688,6 +695,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference", "cudnn"], default="ours")
     ap.add_argument("--graph", choices=["auto", "on", "off", "segmented"], default="auto",
                     help="capture the iteration in a CUDA graph (segmented: the N > 1 form — graphs cut at the exchange points — also at N = 1)")
+    ap.add_argument("--form", choices=["lean", "faithful"], default="lean",
+                    help="configs 3/4/5: skip the backward sweeps the reference's loop body throws away (lean) or replay its sequence call for call")
     ap.add_argument("--collectives", choices=["eager", "captured"], default="eager",
                     help="N > 1: NCCL calls issued eagerly between CUDA graphs (default) or captured inside one graph (experiment)")
     ap.add_argument("--streams", type=int, default=1, help="engine streams (independent branches / weight gradients run concurrently)")

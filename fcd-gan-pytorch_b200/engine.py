@@ -359,6 +359,8 @@ class Tape:
         self.acts: List[Act] = []
         self.pgrads: Dict[int, torch.Tensor] = {}   # id(param) -> grad (this replay)
         self.params: Dict[int, torch.Tensor] = {}
+        self.param_grads = True                     # False: no parameter of the network requires a gradient (a pass that only
+                                                    # carries a gradient THROUGH the network): weight-gradient launches are skipped
         self.forked = False                         # work of this replay is in flight on the side stream
         self.held: List = []                        # buffers that work reads: kept alive until it has been joined
 
@@ -500,15 +502,16 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
                   N, H, W, Cin, Cin_p, Cout, Cout_p, KH, KW, stride, pad, acc, ws.data_ptr(), nbytes, _cfg["engine"],
                   tag=f"conv_wgrad_{eng} {shape}", flops=flops)
 
-        if not frozen:
+        want_w = not frozen and tape.param_grads
+        if want_w:
             gw, acc = tape.pgrad(w)
             gb = None
             if b is not None and not z.db_done:
                 gb, accb = tape.pgrad(b)
                 assert accb == acc
         z.db_done = False
-        side = _cfg["streams"] > 1 and not frozen
-        if not frozen and not side:
+        side = _cfg["streams"] > 1 and want_w
+        if want_w and not side:
             wgrad()
         if x_needs_grad:
             g = x.grad
@@ -564,6 +567,10 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
     def backward(tape):
         dz = z.dz
         assert dz is not None
+        if not tape.param_grads:         # no input gradient here either (the input is data): nothing to do
+            z.db_done = False
+            z.dz = None
+            return
         gw, acc = tape.pgrad(w)
         dwp = torch.empty((Cout, 64, KH, ng), dtype=torch.float32, device=tape.device)
         need_db = b is not None and not z.db_done        # else: delivered by bn_act's backward (fcd_bn_bwd_finalize)
@@ -614,6 +621,10 @@ def conv_im2col_s2(tape: Tape, x: torch.Tensor, w: torch.Tensor, b: Optional[tor
     def backward(tape):
         dz = z.dz
         assert dz is not None
+        if not tape.param_grads:
+            z.db_done = False
+            z.dz = None
+            return
         gw, acc = tape.pgrad(w)
         need_db = b is not None and not z.db_done
         z.db_done = False
@@ -1034,6 +1045,7 @@ class NetFunction(torch.autograd.Function):
                 raise _lib.FcdError("fcdgan_b200 networks take fp32 CUDA tensors (there is no CPU path)")
         record = any(ctx.needs_input_grad[2:])
         tape = Tape(inputs[0].device, record)
+        tape.param_grads = any(ctx.needs_input_grad[2 + n_inputs:])
         with torch.cuda.device(inputs[0].device):       # kernels launch on the TENSORS' device, whatever device is current
             outs, slot, input_acts = runner.fn(tape, inputs, ctx.needs_input_grad[2:2 + n_inputs])
         ctx.tape, ctx.slot, ctx.input_acts = tape, slot, input_acts

@@ -167,3 +167,64 @@ def test_step_drivers_match_golden_and_update_parameters():
     moved = {n: any((p.detach() != q).any().item() for p, q in zip(net.parameters(), before[n]))
              for n, net in (("S", netS), ("D", netD), ("G", netG))}
     assert moved == {"S": True, "D": True, "G": False}, moved
+
+
+def _exchange_grads(step, *args, **kw):
+    """Run a step body with a hook at its gradient-exchange points; -> (output dict, {network id: gradients AT the point where
+    the reference's optimizer step would consume them})."""
+    seen = {}
+
+    def hook(net, wait):
+        seen[id(net)] = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    return step(*args, on_grads=hook, **kw), seen
+
+
+def _same_grads(a, b, what):
+    assert a.keys() == b.keys(), what
+    gmax = max(float(v.abs().max()) for v in b.values())
+    for k in b:
+        scale = max(float(b[k].abs().max()), 1e-3 * gmax)
+        err = float((a[k] - b[k]).abs().max()) / scale
+        assert err < 5e-5, f"{what}: {k} differs by {err:.3g}"      # fp32 atomics of the weight-gradient reductions
+
+
+@pytest.mark.parametrize("kind", ["usss", "rsss", "wsss"])
+def test_lean_steps_give_the_optimizers_the_same_gradients(kind):
+    """`lean=True` skips only the backward sweeps whose results the reference's loop body throws away (steps.py docstring):
+    losses, the change-density map and the BatchNorm running statistics are bit-identical to the faithful call sequence, and
+    every network receives the same gradient at the point where its optimizer step consumes it; with optimizers attached the
+    updated parameters agree."""
+    f = load_golden({"usss": "step_usss.pt", "rsss": "step_rsss.pt", "wsss": "step_wsss.pt"}[kind])
+    C = f["C"]
+    res = {}
+    for lean in (False, True):
+        netG, netS, netD = _nets(C)
+        netS.train(); netD.train()
+        if kind == "usss":
+            netG.train()
+            out, seen = _exchange_grads(fb.usss_step, netG, netS, f["x"].to(DEV), f["y"].to(DEV), fb.CNetLoss(channel=C),
+                                        ssim_weight=f["ssim_w"], l1_weight=f["l1_w"], lean=lean)
+            trained = (netG, netS)
+        elif kind == "rsss":
+            netG.eval()
+            out, seen = _exchange_grads(fb.rsss_step, netG, netS, netD, f["x"].to(DEV), f["y"].to(DEV), f["region"].to(DEV),
+                                        fb.CGeneratorLoss(channel=C), lean=lean)
+            trained = (netD, netS)
+        else:
+            netG.eval()
+            d_w, l1_w, g_w, nc_w, ssim_w = f["weights"]
+            out, seen = _exchange_grads(fb.wsss_step, netG, netS, netD, *(f[k].to(DEV) for k in ("x", "y", "x_nc", "y_nc")),
+                                        fb.CGeneratorLoss(channel=C), d_weight=d_w, l1_weight=l1_w, g_weight=g_w, nc_weight=nc_w,
+                                        ssim_weight=ssim_w, lean=lean)
+            trained = (netD, netS)
+        stats = {k: v.clone() for n in (netG, netS, netD) for k, v in n.state_dict().items() if "running" in k or "num_batches" in k}
+        res[lean] = (out, [seen[id(n)] for n in trained], stats)
+    out0, g0, st0 = res[False]
+    out1, g1, st1 = res[True]
+    for k, v in out0.items():                      # every loss and the change-density map: the forward passes are the same
+        assert torch.equal(v.detach(), out1[k].detach()) or rel_err(out1[k], v) < 1e-6, k
+    for a, b, name in zip(g1, g0, ("first trained network", "second trained network")):
+        _same_grads(a, b, f"{kind} {name}")
+    for k in st0:
+        assert torch.equal(st0[k], st1[k]), k
