@@ -57,6 +57,7 @@ int conv2d_taps_wgrad_tc(const void*, const void*, int, int, int, const void*, c
 extern bool g_wgrad_halo_enabled;
 extern bool g_conv_halo_enabled;
 extern bool g_conv_tma_out;
+extern int g_conv_halo_slots;
 int channel_sum_split(const void* hi, const void* lo, int ld, long long npix, int C, float* out, int accumulate,
                       cudaStream_t stream);
 
@@ -77,6 +78,10 @@ int fcd_set_option(const char* name, int value) {
     }
     if (strcmp(name, "conv_tma_out") == 0) {
         g_conv_tma_out = value != 0;
+        return FCD_OK;
+    }
+    if (strcmp(name, "conv_halo_slots") == 0) {
+        g_conv_halo_slots = value;
         return FCD_OK;
     }
     if (strcmp(name, "conv_halo") == 0) {

@@ -777,6 +777,8 @@ bool conv_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride) {
 
 bool g_conv_halo_enabled = true;    // fcd_set_option("conv_halo", 0) selects the per-tap kernel everywhere
 bool g_conv_tma_out = true;         // fcd_set_option("conv_tma_out", 0): per-thread stores in the halo kernel's epilogue
+int g_conv_halo_slots = 0;          // fcd_set_option("conv_halo_slots", n): cap of the x-plane ring (0 = default); what the ring
+                                    // does not take deepens the epilogue's output staging ring
 
 namespace {
 constexpr int HALO_SMEM_MAX = 227 * 1024 - 1024;   // opt-in limit minus the kernel's static shared memory
@@ -823,6 +825,7 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
         block_n = bn; w_bytes = static_cast<int>(wb);
         nslots = static_cast<int>(room / slot);
         if (nslots > 4) nslots = 4;        // a one-tile look-ahead is all the MMA warp can use; the rest goes to the epilogue
+        if (g_conv_halo_slots >= 2 && nslots > g_conv_halo_slots) nslots = g_conv_halo_slots;
         break;
     }
     if (!block_n) return false;

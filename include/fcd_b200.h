@@ -51,7 +51,9 @@ extern "C" {
 
 const char* fcd_last_error(void);
 int fcd_version(void);
-/* Library-wide switches for A/B measurements: "wgrad_halo" (default 1) = halo-reuse weight-gradient kernel. */
+/* Library-wide switches for A/B measurements: "wgrad_halo" (default 1) = halo-reuse weight-gradient kernel; "conv_halo" (1) =
+ * halo-reuse forward / dgrad kernel; "conv_tma_out" (1) = TMA-store epilogue; "conv_halo_slots" (0 = automatic) = cap of the halo
+ * kernel's input-plane ring (shared memory it does not take deepens the epilogue's output staging ring). */
 int fcd_set_option(const char* name, int value);
 /* 1 if the tcgen05 engine can serve this convolution, else 0 (then AUTO uses SIMT). */
 int fcd_conv2d_tc_supported(int Cin_p, int Cout_p, int KH, int KW, int stride);

@@ -27,8 +27,9 @@ def run(prec):
                   bias.data_ptr() if use_bias else None, z.data_ptr() if use_addend else None, C, z.data_ptr(), C, N, H, W, C, C,
                   3, 3, 1, 1, st[0].data_ptr() if use_stats else None, st[1].data_ptr() if use_stats else None, 0, E._raw_stream())
 
-    for tma in (1, 0):
+    for tma, slots in ((1, 0), (1, 2), (0, 0)):
         _lib.call("fcd_set_option", b"conv_tma_out", tma)
+        _lib.call("fcd_set_option", b"conv_halo_slots", slots)
         for name, args in (("plain", (0, 0, 0)), ("bias", (1, 0, 0)), ("bias+stats", (1, 1, 0)), ("stats", (0, 1, 0)),
                            ("accumulate (dgrad form)", (0, 0, 1))):
             for _ in range(3):
@@ -40,8 +41,9 @@ def run(prec):
                 call(*args)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 20
-            print(f"{prec:6s} tma_out={tma}  {name:26s} {ms * 1e3:7.1f} us   {FL / ms / 1e9:7.1f} TFLOP/s algorithmic", flush=True)
+            print(f"{prec:6s} tma_out={tma} x_slots={slots or 'auto'}  {name:26s} {ms * 1e3:7.1f} us   {FL / ms / 1e9:7.1f} TFLOP/s algorithmic", flush=True)
     _lib.call("fcd_set_option", b"conv_tma_out", 1)
+    _lib.call("fcd_set_option", b"conv_halo_slots", 0)
 
 
 for prec in ("parity", "fast"):
