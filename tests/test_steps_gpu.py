@@ -201,7 +201,7 @@ def _same_grads(a, b, what):
 @pytest.mark.parametrize("kind", ["usss", "rsss", "wsss"])
 def test_lean_steps_give_the_optimizers_the_same_gradients(kind):
     """`lean=True` skips only the backward sweeps whose results the reference's loop body throws away (steps.py docstring):
-    losses, the change-density map and the BatchNorm running statistics are bit-identical to the faithful call sequence, and
+    losses, the change-density map and the BatchNorm running statistics are those of the faithful call sequence, and
     every network receives the same gradient at the point where its optimizer step consumes it; with optimizers attached the
     updated parameters agree."""
     f = load_golden({"usss": "step_usss.pt", "rsss": "step_rsss.pt", "wsss": "step_wsss.pt"}[kind])
@@ -235,5 +235,7 @@ def test_lean_steps_give_the_optimizers_the_same_gradients(kind):
         assert torch.equal(v.detach(), out1[k].detach()) or rel_err(out1[k], v) < 1e-6, k
     for a, b, name in zip(g1, g0, ("first trained network", "second trained network")):
         _same_grads(a, b, f"{kind} {name}")
+    # running statistics: bit-identical for G and S (same forward passes); D's first layer runs on receptive-field-packed rows
+    # when its inputs carry no gradient (the lean D update) and on the zero-padded form otherwise: same numbers to rounding
     for k in st0:
-        assert torch.equal(st0[k], st1[k]), k
+        assert torch.equal(st0[k], st1[k]) or rel_err(st1[k].float(), st0[k].float()) < 1e-5, k
