@@ -420,9 +420,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             int slot = 0;
             uint32_t phase = 0;
             for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
-                long long t = tile;
-                const int tw = static_cast<int>(t % p.tiles_w);
-                t /= p.tiles_w;
+                unsigned t = static_cast<unsigned>(tile);          // 32-bit: four 64-bit divisions per tile were ~9 % of the
+                const int tw = static_cast<int>(t % p.tiles_w);    // fast-precision tile period (ncu r02); pix_tiles < 2^31 is
+                t /= p.tiles_w;                                    // checked on the host
                 const int th = static_cast<int>(t % p.tiles_h);
                 const int n = static_cast<int>(t / p.tiles_h);
                 const int h0 = th * HT_H + hp.box_dh, w0 = tw * HT_W + hp.box_dw;
@@ -508,13 +508,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         uint32_t acc_phase = 0;
         // per-lane statistics accumulators: [32-column chunk] in the per-thread-store epilogue (lane = column),
         // [16-column half] in the TMA-store epilogue (lane % 16 = column)
-        double st_sum[BLOCK_N / 16], st_sq[BLOCK_N / 16];
-#pragma unroll
-        for (int i = 0; i < BLOCK_N / 16; ++i) st_sum[i] = st_sq[i] = 0.0;
+        // Compensated (Kahan) fp32 pairs, not doubles: the F2F.F64 + DADD per half sat on the FP64 pipe with its long latency
+        // in the middle of the epilogue's dependency chain (ncu r02: 13-18 % of the kernel's stall samples were
+        // math_pipe_throttle on exactly those DADDs).  The pair carries ~48 bits, converted to double once, at the end.
+        KahanF st_sum[BLOCK_N / 16], st_sq[BLOCK_N / 16];
         const float* bias = p.bias ? p.bias + nblk * BLOCK_N : nullptr;
         int obuf = 0;
         for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
-            long long t = tile;
+            unsigned t = static_cast<unsigned>(tile);
             const int tw = static_cast<int>(t % p.tiles_w);
             t /= p.tiles_w;
             const int th = static_cast<int>(t % p.tiles_h);
@@ -597,8 +598,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                             }
                             a += __shfl_xor_sync(0xffffffffu, a, 16);
                             b += __shfl_xor_sync(0xffffffffu, b, 16);
-                            st_sum[ci * 2 + half] += static_cast<double>(a);
-                            st_sq[ci * 2 + half] += static_cast<double>(b);
+                            st_sum[ci * 2 + half].add(a);
+                            st_sq[ci * 2 + half].add(b);
                         }
                     }
                 }
@@ -646,8 +647,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                         f[j] = valid ? f[j] : 0.f;
                         sq[j] = f[j] * f[j];
                     }
-                    st_sum[ci] += static_cast<double>(warp_colsum32(f, lane));
-                    st_sq[ci] += static_cast<double>(warp_colsum32(sq, lane));
+                    st_sum[ci].add(warp_colsum32(f, lane));
+                    st_sq[ci].add(warp_colsum32(sq, lane));
                 }
             }
             tc_fence_before();
@@ -662,15 +663,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             if (lane < 16) {
 #pragma unroll
                 for (int h16 = 0; h16 < BLOCK_N / 16; ++h16) {
-                    atomicAdd(p.stat_sum + nblk * BLOCK_N + h16 * 16 + lane, st_sum[h16]);
-                    atomicAdd(p.stat_sqsum + nblk * BLOCK_N + h16 * 16 + lane, st_sq[h16]);
+                    atomicAdd(p.stat_sum + nblk * BLOCK_N + h16 * 16 + lane, st_sum[h16].value());
+                    atomicAdd(p.stat_sqsum + nblk * BLOCK_N + h16 * 16 + lane, st_sq[h16].value());
                 }
             }
         } else if (p.stat_sum) {
 #pragma unroll
             for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
-                atomicAdd(p.stat_sum + nblk * BLOCK_N + ci * 32 + lane, st_sum[ci]);
-                atomicAdd(p.stat_sqsum + nblk * BLOCK_N + ci * 32 + lane, st_sq[ci]);
+                atomicAdd(p.stat_sum + nblk * BLOCK_N + ci * 32 + lane, st_sum[ci].value());
+                atomicAdd(p.stat_sqsum + nblk * BLOCK_N + ci * 32 + lane, st_sq[ci].value());
             }
         }
     }
@@ -882,6 +883,7 @@ static int run_conv_tc(const void* x_hi, const void* x_lo, int x_ld, int XH, int
             hp.c.tiles_w = ceil_div(p.TOW, HT_W);
             hp.c.n_blocks = p.Cout_p / hbn;
             hp.pix_tiles = 1LL * N * hp.c.tiles_h * hp.c.tiles_w;
+            FCD_CHECK_ARG(hp.pix_tiles < (1LL << 31), "conv2d (halo kernel): more than 2^31 pixel tiles");
             hp.c.total_tiles = hp.pix_tiles * hp.c.n_blocks;
             // TMA-store epilogue: dense output pixels, 16-byte aligned rows; the addend (if any) must be the output itself
             CUtensorMap mz = mxh;

@@ -95,6 +95,19 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Compensated fp32 accumulator (Kahan): s - c carries the running sum to ~2^-48 relative without touching the FP64 pipe.
+// (-fmad must not contract these: the operations below are written so that no a*b+c pattern exists.)
+struct KahanF {
+    float s = 0.f, c = 0.f;
+    __device__ __forceinline__ void add(float v) {
+        const float y = __fsub_rn(v, c);
+        const float t = __fadd_rn(s, y);
+        c = __fsub_rn(__fsub_rn(t, s), y);
+        s = t;
+    }
+    __device__ __forceinline__ double value() const { return static_cast<double>(s) - static_cast<double>(c); }
+};
+
 // Activation kinds shared by the BN/activation kernels and the conv epilogues.
 __device__ __forceinline__ float act_fwd(int kind, float u, float slope) {
     switch (kind) {
