@@ -19,6 +19,10 @@ Demo_USSS.py:327) would bake its address into the graph and then free it — eve
 pointer (found in round 2: replays of the RSSS / USSS / WSSS steps faulted as soon as the allocator returned that block to the
 driver).  With the gradients dropped, the capture allocates them from the graph's private pool, where the address stays valid.
 
+The warm-up iterations (and the capture pass does not execute anything) are REAL iterations: optimizers step, BatchNorm
+running statistics and `num_batches_tracked` advance.  Pass `optimizers=` and `restore_after_warmup=True` to have parameters,
+buffers and optimizer state put back, in place, to their values from before the warm-up once the capture is done.
+
 Do not keep autograd-connected tensors of EARLIER iterations (a loss, a change-density map) alive across the capture: they pin
 that iteration's autograd graph, whose AccumulateGrad nodes — created on the stream that iteration ran on — PyTorch then
 re-uses inside the capture, and the cross-stream wait it inserts ("legacy stream depends on a capturing stream") invalidates
@@ -35,6 +39,30 @@ import torch
 from . import engine as E
 
 
+def _snapshot(modules, optimizers):
+    """Values of every parameter / buffer and of every optimizer-state tensor (warm-up iterations are REAL iterations)."""
+    mods = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in modules]
+    opts = [{p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in o.state.items()}
+            for o in optimizers]
+    return mods, opts
+
+
+def _restore(modules, optimizers, snap) -> None:
+    """Write the snapshot back IN PLACE (the graphs hold the addresses); optimizer state that did not exist before the
+    warm-up is zeroed, which is what a freshly constructed Adam / RMSprop state holds."""
+    mods, opts = snap
+    with torch.no_grad():
+        for m, sd in zip(modules, mods):
+            own = m.state_dict()
+            for k, v in sd.items():
+                own[k].copy_(v)
+        for o, old in zip(optimizers, opts):
+            for p, st in o.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.copy_(old[p][k]) if p in old and k in old[p] else v.zero_()
+
+
 def _drop_grads(modules) -> None:
     for m in modules:
         for p in m.parameters():
@@ -43,9 +71,11 @@ def _drop_grads(modules) -> None:
 
 class GraphedStep:
     def __init__(self, fn: Callable, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 capture_error_mode: str = "global", modules: Sequence[torch.nn.Module] = ()):
+                 capture_error_mode: str = "global", modules: Sequence[torch.nn.Module] = (),
+                 optimizers: Sequence[torch.optim.Optimizer] = (), restore_after_warmup: bool = False):
         self.fn = fn
         self.static_inputs = list(static_inputs)
+        snap = _snapshot(modules, optimizers) if restore_after_warmup else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -62,6 +92,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.outputs = fn(*self.static_inputs)
         self.launches_per_replay = E.launch_count - n0      # libfcd_b200 C-ABI calls recorded in the graph
+        if snap is not None:
+            _restore(modules, optimizers, snap)
         E.bump_weight_epoch()
 
     def copy_inputs(self, *tensors: torch.Tensor) -> None:
@@ -71,66 +103,6 @@ class GraphedStep:
     def __call__(self):
         self.graph.replay()
         E.bump_weight_epoch()      # parameters changed on the device without their version counters moving
-        return self.outputs
-
-
-class SegmentedStep:
-    """An iteration captured as SEVERAL CUDA graphs with eager calls in between — the multi-GPU form: collectives stay
-    outside the graphs (capturing NCCL all-reduces inside one graph hung on this stack), everything else is
-    replayed.
-
-        step = SegmentedStep([seg_g, seg_d, seg_opt], [launch_g, launch_d_and_wait], static_inputs)
-
-    `segments[i](*static_inputs)` are captured one after the other into graphs that share one memory pool (tensors made
-    in one segment stay valid in the next); `between[i]()` runs eagerly after segment i on every call.  Replay order:
-    graph 0, between 0, graph 1, between 1, ..., graph n-1."""
-
-    def __init__(self, segments: Sequence[Callable], between: Sequence[Callable], static_inputs: Sequence[torch.Tensor],
-                 warmup: int = 3, capture_error_mode: str = "thread_local"):
-        assert len(between) == len(segments) - 1
-        self.segments, self.between = list(segments), list(between)
-        self.static_inputs = list(static_inputs)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        torch.cuda.empty_cache()
-        self.graphs, self.outputs = [], []
-        n0 = E.launch_count
-        pool = None
-        for i, seg in enumerate(self.segments):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, capture_error_mode=capture_error_mode):
-                self.outputs.append(seg(*self.static_inputs))
-            pool = g.pool()
-            self.graphs.append(g)
-            if i < len(self.between):
-                self.between[i]()           # keeps the backend's call sequence identical on every rank during set-up
-        self.launches_per_replay = E.launch_count - n0
-        torch.cuda.synchronize()
-        E.bump_weight_epoch()
-
-    def _eager(self):
-        outs = []
-        for i, seg in enumerate(self.segments):
-            outs.append(seg(*self.static_inputs))
-            if i < len(self.between):
-                self.between[i]()
-        return outs
-
-    def copy_inputs(self, *tensors: torch.Tensor) -> None:
-        for dst, src in zip(self.static_inputs, tensors):
-            dst.copy_(src, non_blocking=True)
-
-    def __call__(self):
-        for i, g in enumerate(self.graphs):
-            g.replay()
-            if i < len(self.between):
-                self.between[i]()
-        E.bump_weight_epoch()
         return self.outputs
 
 
@@ -147,11 +119,13 @@ class YieldingStep:
     """
 
     def __init__(self, genfn: Callable, sync, static_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 capture_error_mode: str = "thread_local", modules: Sequence[torch.nn.Module] = ()):
+                 capture_error_mode: str = "thread_local", modules: Sequence[torch.nn.Module] = (),
+                 optimizers: Sequence[torch.optim.Optimizer] = (), restore_after_warmup: bool = False):
         from .steps import drive
 
         self.sync = sync
         self.static_inputs = list(static_inputs)
+        snap = _snapshot(modules, optimizers) if restore_after_warmup else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -199,6 +173,8 @@ class YieldingStep:
                 self.actions.append((net, wait))
         self.launches_per_replay = E.launch_count - n0
         torch.cuda.synchronize()
+        if snap is not None:
+            _restore(modules, optimizers, snap)
         E.bump_weight_epoch()
 
     def copy_inputs(self, *tensors: torch.Tensor) -> None:

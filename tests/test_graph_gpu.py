@@ -7,7 +7,6 @@ Tolerance of the loss trajectory: the weight-gradient reductions use fp32 atomic
 not bit-identical either; Adam / RMSprop turn a gradient element at that noise level into a full lr-sized step of either sign,
 and the losses of iterations 2, 3 inherit it.  The test measures that run-to-run spread (two eager runs) and holds the graph
 replays to max(3e-5, 4 x spread) relative — the first iteration, which no optimizer step precedes, to 1e-6."""
-import copy
 import re
 
 import pytest
@@ -112,15 +111,15 @@ def _graph_replay_matches_eager(form):
     # graph run from the same initial state; the warm-up iterations of the capture advance the optimizers too, so the
     # initial state is restored after the capture
     netG, netD, optG, optD, x, y, cmap, zero = _setup()
-    state = (copy.deepcopy(netG.state_dict()), copy.deepcopy(netD.state_dict()))
     seg_g, seg_d, seg_opt = _segments(netG, netD, optG, optD, zero)
+    kw = dict(warmup=2, modules=[netG, netD], optimizers=[optG, optD], restore_after_warmup=True)
     if form == "whole":
         def whole(x, y, cmap):
             gl, dl = seg_g(x, y, cmap), seg_d(x, y, cmap)
             seg_opt(x, y, cmap)
             return gl, dl
 
-        step = GraphedStep(whole, [x, y, cmap], warmup=2)
+        step = GraphedStep(whole, [x, y, cmap], **kw)
     else:
         def gen(x, y, cmap):
             gl = seg_g(x, y, cmap)
@@ -130,21 +129,12 @@ def _graph_replay_matches_eager(form):
             seg_opt(x, y, cmap)
             return gl, dl
 
-        step = YieldingStep(gen, GradSync(), [x, y, cmap], warmup=2)
+        step = YieldingStep(gen, GradSync(), [x, y, cmap], **kw)
         assert len(step.graphs) == 3
     run = lambda: step()
     assert step.launches_per_replay > 50
-    # restore IN PLACE (the graphs hold the parameter / optimizer-state addresses)
-    with torch.no_grad():
-        for net, sd in ((netG, state[0]), (netD, state[1])):
-            own = net.state_dict()
-            for k, v in sd.items():
-                own[k].copy_(v)
-        for opt in (optG, optD):                 # fresh optimizer state = zeros (step counters and moment estimates)
-            for st in opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+    # (the warm-up iterations of the capture advanced parameters, running statistics and optimizer state: restore_after_warmup
+    # put them back in place)
     for i in range(steps):
         gl, dl = run()
         t = 1e-6 if i == 0 else tol
@@ -202,23 +192,13 @@ def test_rsss_step_graph_forms_match_eager(form):
     again = [pick(S.drive(gen(*data))) for _ in range(steps)]
     spread = max(abs(a - b) / max(1.0, abs(a)) for la, lb in zip(eager, again) for a, b in zip(la, lb))
     nets, opts, gen, data = setup()
-    state = [copy.deepcopy(n.state_dict()) for n in nets]
+    kw = dict(warmup=2, modules=nets, optimizers=opts, restore_after_warmup=True)
     if form == "whole":
-        step = GraphedStep(lambda *a: S.drive(gen(*a)), data, warmup=2, modules=nets)
+        step = GraphedStep(lambda *a: S.drive(gen(*a)), data, **kw)
     else:
-        step = YieldingStep(gen, GradSync(), data, warmup=2, modules=nets)
+        step = YieldingStep(gen, GradSync(), data, **kw)
         assert len(step.graphs) == 3
     torch.cuda.empty_cache()
-    with torch.no_grad():
-        for net, sd in zip(nets, state):
-            own = net.state_dict()
-            for k, v in sd.items():
-                own[k].copy_(v)
-        for opt in opts:
-            for st in opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
     junk = torch.full((64 << 20,), float("nan"), device=DEV)     # whatever the allocator hands out next must not alias graph memory
     for i in range(steps):
         got = pick(step())
