@@ -309,12 +309,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 //     moved by (r * halo_w + s) pixels, stride-byte-offset = halo_w * 128 so the 8-pixel groups follow the halo row pitch
 //     (semantics pinned on the device by scripts/probe_halo.py);
 //   * split precision stages the hi and lo planes as separate ring items: all taps of x_hi * [w_hi ; w_lo] (N = 2*BLOCK_N),
-//     then all taps of x_lo * w_hi (N = BLOCK_N), so three plane slots are enough for a one-tile look-ahead.
+//     then all taps of x_lo * w_hi (N = BLOCK_N); two plane slots (one multiplied, one in flight) keep the MMA warp fed.
 // L2 -> shared traffic per pixel tile drops from taps * 48 KB to 2 * 23 KB for a 3x3 64->64 layer.
 // The BatchNorm statistics are accumulated in registers across the CTA's tiles (butterfly column sums, fp32 per 32 pixels,
 // double across tiles) and flushed with one double atomic per (warp, channel) at the end.
 // =====================================================================================================================
 constexpr int HT_H = 16, HT_W = 8;      // pixel tile of the halo kernel (M = 128 = 16 groups of 8 pixels)
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 and 6-9 TWO epilogue warpgroups: group g drains TMEM accumulator g, i.e.
+// every other pixel tile.  One group needs ~3300 cycles per tile (tcgen05.ld -> bias -> staging -> TMA store -> statistics, a
+// chain of latencies), the MMA of a tile 1728 (single-pass bf16) / 4032 (split) cycles: with one group the single-pass kernel
+// was epilogue-bound at 24 % tensor-pipe activity (ncu r02).
+constexpr int HALO_EPI_GROUPS = 2;
+constexpr int HALO_THREADS = 64 + HALO_EPI_GROUPS * 128;
 
 struct ConvHaloParams {
     ConvTcParams c;
@@ -345,7 +351,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 template <int BLOCK_N, bool SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const __grid_constant__ CUtensorMap map_z, const ConvHaloParams hp) {
@@ -366,7 +372,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* w_bar = tmem_empty + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_bar + 1);
-    uint8_t* out_stage = xsm + hp.nslots * hp.slot_bytes + 1024;     // 4 epilogue warps x 2 KB (32 pixels x 16 fp32 channels)
+    uint8_t* out_stage = xsm + hp.nslots * hp.slot_bytes + 1024;     // 8 epilogue warps x out_bufs x 2 KB (32 pixels x 16 fp32 channels)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -504,8 +510,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int lh = row / HT_W, lw = row - lh * HT_W;
-        int acc = 0;
+        const int egroup = (warp - EPI_WARP0) >> 2;     // this warp's epilogue group = the TMEM accumulator it drains
+        const int acc = egroup;
         uint32_t acc_phase = 0;
+        int it = 0;
         // per-lane statistics accumulators: [32-column chunk] in the per-thread-store epilogue (lane = column),
         // [16-column half] in the TMA-store epilogue (lane % 16 = column)
         // Compensated (Kahan) fp32 pairs, not doubles: the F2F.F64 + DADD per half sat on the FP64 pipe with its long latency
@@ -514,7 +522,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         KahanF st_sum[BLOCK_N / 16], st_sq[BLOCK_N / 16];
         const float* bias = p.bias ? p.bias + nblk * BLOCK_N : nullptr;
         int obuf = 0;
-        for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step) {
+        for (long long tile = tile0; tile < hp.pix_tiles; tile += tile_step, ++it) {
+            if ((it & 1) != egroup) continue;               // the other group's tile
             unsigned t = static_cast<unsigned>(tile);
             const int tw = static_cast<int>(t % p.tiles_w);
             t /= p.tiles_w;
@@ -533,7 +542,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 // go through a 2 KB staging buffer (64B-swizzled rows, conflict-free 16-byte writes) and leave as ONE bulk
                 // tensor store {16 ch, 8 w, 4 h}: full 64-byte segments instead of 32 scattered 16-byte stores per instruction,
                 // out-of-image pixels clipped by the TMA unit, in-place accumulation as a reduce-add.
-                uint8_t* stage_ring = out_stage + q * hp.out_bufs * 2048;
+                uint8_t* stage_ring = out_stage + (egroup * 4 + q) * hp.out_bufs * 2048;
                 const int oh0 = th * HT_H + q * 4, ow0 = tw * HT_W;
 #pragma unroll
                 for (int ci = 0; ci < BLOCK_N / 32; ++ci) {
@@ -603,10 +612,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                         }
                     }
                 }
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
-                }
+                acc_phase ^= 1u;
                 continue;
             }
 #pragma unroll
@@ -653,10 +659,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1u;
-            }
+            acc_phase ^= 1u;
         }
         if (hp.tma_out && lane == 0) tma_store_wait_all();
         if (p.stat_sum && hp.tma_out) {
@@ -797,13 +800,13 @@ static int launch_conv_halo(const CUtensorMap& mxh, const CUtensorMap& mxl, cons
     long long grid = sm_count() / hp.c.n_blocks * hp.c.n_blocks;
     if (grid < hp.c.n_blocks) grid = hp.c.n_blocks;
     if (grid > hp.pix_tiles * hp.c.n_blocks) grid = hp.pix_tiles * hp.c.n_blocks;
-    conv_halo_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, NUM_THREADS, smem_bytes, stream>>>(mxh, mxl, mwh, mwl, mz, hp);
+    conv_halo_kernel<BLOCK_N, SPLIT><<<(unsigned)grid, HALO_THREADS, smem_bytes, stream>>>(mxh, mxl, mwh, mwl, mz, hp);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
 
 // Fills hp and returns true when the halo kernel takes this launch: stride-1 reads, every tap view inside one TMA box, and the
-// CTA's weight block resident in shared memory next to >= 3 (split) / 2 plane slots.
+// CTA's weight block resident in shared memory next to >= 2 plane slots and the two epilogue groups' staging rings.
 static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, int* block_n_out, ConvHaloParams* hp,
                            int* smem_bytes) {
     if (!g_conv_halo_enabled || csh != 1 || csw != 1 || p.n_r * p.n_s < 1) return false;
@@ -815,13 +818,13 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
     const int slot = (x_bytes + 1023) & ~1023;
     const int planes = split ? 2 : 1;
     const int cchunks = p.Cin_p / BLOCK_K;
-    const int min_slots = split ? 3 : 2;
+    const int min_slots = 2;      // hi / lo planes alternate: one being multiplied, one in flight (a third slot measured no gain)
     int block_n = 0, nslots = 0, w_bytes = 0;
     for (int bn : {128, 64}) {
         if (p.Cout_p % bn) continue;
         if (split && bn == 128) continue;                      // 2 * (2 * 128) accumulator columns would need all of TMEM
         const long long wb = 1LL * p.n_r * p.n_s * cchunks * planes * bn * 128;
-        const long long room = HALO_SMEM_MAX - 1024 - 1024 - 4 * 2048 - wb;    // alignment slack, barriers, minimal output staging
+        const long long room = HALO_SMEM_MAX - 1024 - 1024 - HALO_EPI_GROUPS * 4 * 2048 - wb;    // alignment slack, barriers, minimal output staging
         if (room < 1LL * min_slots * slot) continue;
         block_n = bn; w_bytes = static_cast<int>(wb);
         nslots = static_cast<int>(room / slot);
@@ -837,10 +840,11 @@ static bool conv_halo_plan(const ConvTcParams& p, bool split, int csh, int csw, 
     hp->box_dh = p.dh0 + min_dh; hp->box_dw = p.dw0 + min_dw;
     hp->off_h0 = -min_dh; hp->off_w0 = -min_dw;
     *block_n_out = block_n;
-    // whatever is left after the weights and the x ring deepens the epilogue's staging ring (4 warps x out_bufs x 2 KB)
+    // whatever is left after the weights and the x ring deepens the epilogue's staging ring (8 warps x out_bufs x 2 KB)
     const long long left = HALO_SMEM_MAX - 1024 - 1024 - w_bytes - 1LL * nslots * slot;
-    hp->out_bufs = left >= 4 * 4 * 2048 ? 4 : left >= 2 * 4 * 2048 ? 2 : 1;
-    *smem_bytes = w_bytes + nslots * slot + 1024 + 1024 + 4 * hp->out_bufs * 2048;
+    constexpr int EW = HALO_EPI_GROUPS * 4;
+    hp->out_bufs = left >= 4 * EW * 2048 ? 4 : left >= 2 * EW * 2048 ? 2 : 1;
+    *smem_bytes = w_bytes + nslots * slot + 1024 + 1024 + EW * hp->out_bufs * 2048;
     return true;
 }
 

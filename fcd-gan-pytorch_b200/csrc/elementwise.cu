@@ -125,25 +125,24 @@ __global__ void stage_im2col_s2_kernel(const float* __restrict__ src, int C, int
             im_tile[rc * IM_W + x] = (row_in && iw >= 0 && iw < W) ? __ldg(line + iw) : 0.f;
         }
     }
+    // k -> offset of (tap row, channel, tap column) inside the staged tile (or -1 for the zero padding k >= 9*C): computed once
+    // per block instead of a division chain per element
+    int* lut = reinterpret_cast<int*>(im_tile + 3 * C * IM_W);
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        const int tap = k / C, c = k - tap * C;
+        const int tr = tap / 3, ts = tap - tr * 3;
+        lut[k] = tap < 9 ? (tr * C + c) * IM_W + ts : -1;
+    }
     __syncthreads();
     const int kg = Kp / 8;
     for (int slot = threadIdx.x; slot < ST_PIX * kg; slot += blockDim.x) {
         const int i = slot / kg, k0 = (slot - i * kg) * 8;
         if (ow0 + i >= OW) continue;
         F8 r;
-        int tap = k0 / C, c = k0 - tap * C;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = 0.f;
-            if (tap < 9) {
-                const int tr = tap / 3, ts = tap - tr * 3;
-                v = im_tile[(tr * C + c) * IM_W + 2 * i + ts];
-            }
-            r.v[j] = v;
-            if (++c == C) {
-                c = 0;
-                ++tap;
-            }
+            const int off = lut[k0 + j];
+            r.v[j] = off >= 0 ? im_tile[off + 2 * i] : 0.f;
         }
         const size_t pix = (static_cast<size_t>(n) * OH + oh) * OW + ow0 + i;
         st_split8(hi, lo, pix * Kp + k0, r);
@@ -796,7 +795,7 @@ int fcd_stage_im2col3x3s2(const float* src, int N, int C, int H, int W, void* ds
     FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= 9 * C, "fcd_stage_im2col3x3s2: Kp must be a multiple of 8 and >= 9*C");
     const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
     FCD_CHECK_ARG(N <= 65535 && OH <= 65535, "fcd_stage_im2col3x3s2: dims exceed the launch grid");
-    const size_t smem = sizeof(float) * 3 * C * (2 * ST_PIX + 1);
+    const size_t smem = sizeof(float) * 3 * C * (2 * ST_PIX + 1) + sizeof(int) * Kp;       // staged tile + k -> offset table
     FCD_CHECK_ARG(smem <= 48 * 1024, "fcd_stage_im2col3x3s2: too many channels (%d)", C);
     stage_im2col_s2_kernel<<<dim3((OW + ST_PIX - 1) / ST_PIX, OH, N), NT, smem, as_stream(stream)>>>(src, C, H, W, OH, OW, Kp,
                                                                                                   BF(dst_hi), BF(dst_lo));
