@@ -75,6 +75,11 @@ def load():
         fn.argtypes = argtypes
         fn.restype = restype
     _lib = lib
+    # A/B switches without code changes: FCD_OPTIONS="conv_halo=0,conv_tma_out=0" (see fcd_set_option in the header)
+    for item in filter(None, os.environ.get("FCD_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        if lib.fcd_set_option(name.strip().encode(), int(value or 1)) != 0:
+            raise FcdError(f"FCD_OPTIONS: {lib.fcd_last_error().decode(errors='replace')}")
     return lib
 
 

@@ -3,10 +3,13 @@ N = 1) and the same iteration cut into several graphs at its gradient-exchange p
 here on one GPU, where the exchange between the graphs is a no-op) must produce what the iteration produces when issued
 eagerly: same loss trajectory, same parameters after several optimizer steps.
 
-Tolerance of the loss trajectory: the weight-gradient reductions use fp32 atomics, so two EAGER runs from the same state are
-not bit-identical either; Adam / RMSprop turn a gradient element at that noise level into a full lr-sized step of either sign,
-and the losses of iterations 2, 3 inherit it.  The test measures that run-to-run spread (two eager runs) and holds the graph
-replays to max(3e-5, 4 x spread) relative — the first iteration, which no optimizer step precedes, to 1e-6."""
+Tolerance of the loss trajectory: the first iteration, which no optimizer step precedes, must agree to 1e-6.  Later iterations
+inherit the optimizers' amplification of gradient noise: the weight-gradient reductions use fp32 atomics, so two EAGER runs from
+the same state are not bit-identical either, and Adam / RMSprop turn a gradient element at that noise level into a full lr-sized
+step of either sign.  The test measures that run-to-run spread (two eager runs) and holds the replays to max(3e-4, 4 x spread)
+relative: the spread of one pair of runs is itself a random draw (measured 1e-6 ... 1e-4 over many runs), so the floor is what
+round 1 arrived at empirically; a wrong graph (a dangling gradient buffer, a missing segment) is off by orders of magnitude
+more or not finite at all."""
 import re
 
 import pytest
@@ -107,7 +110,7 @@ def _graph_replay_matches_eager(form):
     eager_losses, want = _eager_run(steps)
     eager_again, _ = _eager_run(steps)
     spread = max(abs(a - b) / max(1.0, abs(a)) for la, lb in zip(eager_losses, eager_again) for a, b in zip(la, lb))
-    tol = max(3e-5, 4 * spread)
+    tol = max(3e-4, 4 * spread)
     # graph run from the same initial state; the warm-up iterations of the capture advance the optimizers too, so the
     # initial state is restored after the capture
     netG, netD, optG, optD, x, y, cmap, zero = _setup()
@@ -202,7 +205,7 @@ def test_rsss_step_graph_forms_match_eager(form):
     junk = torch.full((64 << 20,), float("nan"), device=DEV)     # whatever the allocator hands out next must not alias graph memory
     for i in range(steps):
         got = pick(step())
-        t = 1e-6 if i == 0 else max(3e-5, 4 * spread)
+        t = 1e-6 if i == 0 else max(3e-4, 4 * spread)
         for a, b in zip(got, eager[i]):
             assert abs(a - b) <= t * max(1.0, abs(b)), (form, i, got, eager[i], spread)
     assert torch.isnan(junk).all()

