@@ -380,12 +380,17 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ da, int da_ld
 __global__ void bn_bwd_finalize_kernel(const double* s1, const double* s2, double count, int train, int C, int Cp,
                                        float* c1, float* c2, float* dgamma, float* dbeta, int accumulate,
                                        const double* ds, float* dslope, const float* scale, const double* zsum,
-                                       const float* mean, const float* invstd, float* dbias, int dbias_accumulate) {
+                                       const float* mean, const float* invstd, float* dbias, int dbias_accumulate,
+                                       const double* gs1, const double* gs2, double gcount) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && dslope) *dslope = (accumulate ? *dslope : 0.f) + static_cast<float>(*ds);
     if (c >= Cp) return;
-    const float k1 = (train && c < C) ? static_cast<float>(s1[c] / count) : 0.f;
-    const float k2 = (train && c < C) ? static_cast<float>(s2[c] / count) : 0.f;
+    // the means that enter dz are those of the WHOLE batch the statistics were taken over: the local sums, or (SyncBN) the sums
+    // over all ranks; parameter gradients always come from the LOCAL sums (the gradient exchange averages them afterwards)
+    const double m1 = gs1 ? gs1[c] / gcount : s1[c] / count;
+    const double m2 = gs2 ? gs2[c] / gcount : s2[c] / count;
+    const float k1 = (train && c < C) ? static_cast<float>(m1) : 0.f;
+    const float k2 = (train && c < C) ? static_cast<float>(m2) : 0.f;
     c1[c] = k1;
     c2[c] = k2;
     if (c < C) {
@@ -404,7 +409,6 @@ __global__ void bn_bwd_finalize_kernel(const double* s1, const double* s2, doubl
     }
 }
 
-// dz = scale * (dy - c1 - xhat * c2), dy = da * act'(u);  written split (operand of dgrad / wgrad).
 // A thread owns ONE 8-channel group and walks APPLY_PIX pixels with it, so the six per-channel vectors are loaded once per
 // thread instead of once per pixel (they were 12 of the 16 load instructions of the one-pixel form).
 constexpr int APPLY_PIX = 4;
@@ -904,11 +908,15 @@ int fcd_bn_act_bwd_reduce(const float* da, int da_ld, const float* z, int z_ld, 
 int fcd_bn_bwd_finalize(const double* s1, const double* s2, double count, int training, int C, int Cp, float* c1,
                         float* c2, float* dgamma, float* dbeta, int accumulate, const double* ds, float* dslope,
                         const float* scale, const double* zsum, const float* mean, const float* invstd, float* dbias,
-                        int dbias_accumulate, void* stream) {
+                        int dbias_accumulate, const double* global_s1, const double* global_s2, double global_count,
+                        void* stream) {
     FCD_CHECK_ARG(s1 && s2 && c1 && c2 && count > 0, "fcd_bn_bwd_finalize: bad arguments");
+    FCD_CHECK_ARG((global_s1 == nullptr) == (global_s2 == nullptr) && (!global_s1 || global_count > 0),
+                  "fcd_bn_bwd_finalize: global sums go together with a positive global count");
     bn_bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, as_stream(stream)>>>(s1, s2, count, training, C, Cp, c1, c2,
                                                                             dgamma, dbeta, accumulate, ds, dslope, scale,
-                                                                            zsum, mean, invstd, dbias, dbias_accumulate);
+                                                                            zsum, mean, invstd, dbias, dbias_accumulate,
+                                                                            global_s1, global_s2, global_count);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

@@ -28,7 +28,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
 BN_MOMENTUM = 0.1
 
-_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1}
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1, "sync_bn": None}
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_g2.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
@@ -53,6 +53,30 @@ def set_streams(n: int) -> None:
 
 def get_streams() -> int:
     return _cfg["streams"]
+
+
+def set_sync_bn(enabled: bool, group=None) -> None:
+    """Synchronised BatchNorm for data-parallel runs (no reference counterpart — the reference is single-device; SURVEY.md
+    §8(e)): every train-mode BatchNorm call all-reduces its batch sums (2*C doubles forward, 2*C doubles backward) over
+    `group`, so an N-rank run with equal shards computes exactly the statistics, running statistics and gradients of the
+    single-process run on the concatenated batch.  Off by default (per-rank statistics, the DDP default)."""
+    import torch.distributed as dist
+
+    if enabled and not dist.is_initialized():
+        raise RuntimeError("set_sync_bn(True) needs an initialised torch.distributed process group")
+    _cfg["sync_bn"] = (group,) if enabled else None
+
+
+def _sync_world() -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size(_cfg["sync_bn"][0]) if _cfg["sync_bn"] is not None else 1
+
+
+def _all_reduce_sum(t: torch.Tensor) -> None:
+    import torch.distributed as dist
+
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_cfg["sync_bn"][0])
 
 
 def get_precision() -> str:
@@ -169,11 +193,13 @@ class Act:
 class Z:
     """fp32 NHWC convolution output + BatchNorm statistics."""
 
-    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "dz", "pack_m", "bias_param", "db_done")
+    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "stats", "sum_local", "dz", "pack_m", "bias_param", "db_done")
 
     def __init__(self, t, N, H, W, C, Cp):
         self.t, self.N, self.H, self.W, self.C, self.Cp, self.ld = t, N, H, W, C, Cp, Cp
         self.sum = self.sqsum = None
+        self.stats = None        # the (2, Cp) double tensor behind sum / sqsum (SyncBN all-reduces it in one call)
+        self.sum_local = None    # SyncBN: this rank's own sum, kept for the closed-form conv-bias gradient
         self.bias_param = None   # the producing convolution's bias: bn_act's backward may deliver its gradient (db_done)
         self.db_done = False
         self.dz: Optional[Act] = None
@@ -479,7 +505,7 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     fuse = stats and _cfg["fuse_stats"]
     if stats:
         st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
-        z.sum, z.sqsum = st[0], st[1]
+        z.sum, z.sqsum, z.stats = st[0], st[1], st
     eng = _conv_engine_name(Cin_p, Cout_p, KH, KW, stride)
     flops = 2.0 * N * OH * OW * Cout * Cin * KH * KW          # algorithmic (un-padded) multiply-adds x 2
     shape = f"{KH}x{KW}s{stride} {Cin}->{Cout}"
@@ -560,7 +586,7 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
           tag=f"conv_fwd_tc_pack4 {shape}", flops=flops)
     if stats:
         st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
-        z.sum, z.sqsum = st[0], st[1]
+        z.sum, z.sqsum, z.stats = st[0], st[1], st
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
     z.bias_param = b
 
@@ -722,9 +748,14 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
     vec = None
     if bn is not None:
         vec = torch.empty((6, Cp), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd, c1, c2
+        count = float(npix)
         if training:
             assert z.sum is not None
-        _call("fcd_bn_finalize", _lib.ptr(z.sum), _lib.ptr(z.sqsum), float(npix), bn.weight.data_ptr(),
+            if _cfg["sync_bn"] is not None and z.sum_local is None:      # statistics of the whole (all-rank) batch
+                z.sum_local = z.sum.clone()
+                _all_reduce_sum(z.stats)
+            count = float(npix) * _sync_world()
+        _call("fcd_bn_finalize", _lib.ptr(z.sum), _lib.ptr(z.sqsum), count, bn.weight.data_ptr(),
               bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), C, Cp, BN_MOMENTUM, BN_EPS,
               1 if training else 0, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr())
         if training and bn.num_batches_tracked is not None:
@@ -762,11 +793,18 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
                 gb, acc_b = tape.pgrad(z.bias_param)
                 z.db_done = True
             use_stats = bn is not None and training and z.sum is not None
+            zsum = z.sum
+            gl = None
+            if use_stats and z.sum_local is not None:        # SyncBN: dz needs the means over ALL ranks' batches
+                zsum = z.sum_local
+                gl = red[:, :Cp].contiguous()
+                _all_reduce_sum(gl)
             _call("fcd_bn_bwd_finalize", s1.data_ptr(), s2.data_ptr(), float(npix), 1 if (training and bn is not None) else 0,
                   C, Cp, c[4].data_ptr(), c[5].data_ptr(), _lib.ptr(dgam), _lib.ptr(dbet), acc,
                   ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl),
-                  v(0), z.sum.data_ptr() if use_stats else None, v(2) if use_stats else None, v(3) if use_stats else None,
-                  _lib.ptr(gb), acc_b or 0)
+                  v(0), zsum.data_ptr() if use_stats else None, v(2) if use_stats else None, v(3) if use_stats else None,
+                  _lib.ptr(gb), acc_b or 0, None if gl is None else gl[0].data_ptr(), None if gl is None else gl[1].data_ptr(),
+                  float(npix) * _sync_world())
         _call("fcd_bn_act_bwd_apply", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
               sp, slope_const, dz.p_hi(), dz.p_lo(), dz.ld, npix, Cp)
         z.dz = dz

@@ -165,13 +165,16 @@ int fcd_bn_act_fwd(const float* z, int z_ld, const float* scale, const float* sh
 int fcd_bn_act_bwd_reduce(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
                           const float* mean, const float* invstd, int act, const float* slope_ptr, float slope_const,
                           long long npix, int Cp, double* s1, double* s2, double* dslope, void* stream);
-/* dbias (optional): gradient of the producing convolution's bias in closed form from the same sums,
+/* global_s1 / global_s2 / global_count (optional, SyncBN — no reference counterpart): the sums over ALL ranks'
+ * batches; c1, c2 (the means that enter dz) then come from them, the parameter gradients still from the local sums.
+ * dbias (optional): gradient of the producing convolution's bias in closed form from the same sums,
  * scale * (s1 - count*c1 - c2 * sum xhat) with sum xhat = (zsum - count*mean) * invstd (scale null: s1); (+)= when
  * dbias_accumulate. */
 int fcd_bn_bwd_finalize(const double* s1, const double* s2, double count, int training, int C, int Cp, float* c1,
                         float* c2, float* dgamma, float* dbeta, int accumulate, const double* ds, float* dslope,
                         const float* scale, const double* zsum, const float* mean, const float* invstd, float* dbias,
-                        int dbias_accumulate, void* stream);
+                        int dbias_accumulate, const double* global_s1, const double* global_s2, double global_count,
+                        void* stream);
 int fcd_bn_act_bwd_apply(const float* da, int da_ld, const float* z, int z_ld, const float* scale, const float* shift,
                          const float* mean, const float* invstd, const float* c1, const float* c2, int act,
                          const float* slope_ptr, float slope_const, void* dz_hi, void* dz_lo, int dz_ld, long long npix,
