@@ -13,14 +13,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_step_equals_full_batch_step():
+@pytest.mark.parametrize("mode", ["eval_bn", "sync_bn"])
+def test_sharded_step_equals_full_batch_step(mode):
+    """eval_bn: BatchNorm on running statistics (samples independent).  sync_bn: train-mode BatchNorm with
+    `set_sync_bn(True)` — the N-rank run reproduces the single-process run on the concatenated batch, running statistics
+    included ('SyncBN when global-batch parity with a single-process reference run is required')."""
     env = dict(os.environ, FCD_DIST_TIMEOUT_S="120")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                          "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_dp_equiv.py")],
+                          "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_dp_equiv.py")] +
+                         (["--sync-bn"] if mode == "sync_bn" else []),
                          capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
     if res.returncode != 0 or "DP_EQUIV_OK" not in res.stdout:           # keep the whole transcript where gpurun brings it back
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "dp_equiv_failure.log"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"dp_equiv_failure_{mode}.log"), "w") as fh:
             fh.write(res.stdout + "\n---- stderr ----\n" + res.stderr)
     assert res.returncode == 0 and "DP_EQUIV_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])
     print(res.stdout.strip().splitlines()[-1])
