@@ -83,6 +83,7 @@ def main():
     # (losses are detached at once: a live loss keeps its iteration's autograd graph — and with it the AccumulateGrad nodes
     # created on THIS stream — alive, and a later CUDA-graph capture would re-use those nodes across streams; graph.py docstring)
     gl_full, dl_full = (v.detach() for v in drive(make_gen(netG, netD)(x.to(dev), y.to(dev), cmap.to(dev))))
+    print(f"[rank {rank}] full-batch reference done", file=sys.stderr, flush=True)
     want = grads(netG, netD)
     want_stats = {k: v.clone() for n in (netG, netD) for k, v in n.state_dict().items() if "running" in k}
     # N-rank sharded, eager exchange
@@ -93,12 +94,18 @@ def main():
     gl, dl = (v.detach() for v in drive(make_gen(netG, netD)(xs, ys, cs), sync.on_grads))
     got_eager = grads(netG, netD)
     got_stats = {k: v.clone() for n in (netG, netD) for k, v in n.state_dict().items() if "running" in k}
-    # N-rank sharded, CUDA graphs cut at the exchange points
-    step = YieldingStep(make_gen(netG, netD), sync, [xs, ys, cs], warmup=2, modules=[netG, netD])
-    assert len(step.graphs) == 3
-    step()
-    torch.cuda.synchronize()
-    got_graph = grads(netG, netD)
+    print(f"[rank {rank}] eager exchange done", file=sys.stderr, flush=True)
+    # N-rank sharded, CUDA graphs cut at the exchange points (eval-mode BatchNorm only: SyncBN's all-reduces inside captured
+    # segments mixed with eager all-reduces between them is not a validated combination — SyncBN runs are eager)
+    if SYNC_BN:
+        got_graph = got_eager
+    else:
+        step = YieldingStep(make_gen(netG, netD), sync, [xs, ys, cs], warmup=2, modules=[netG, netD])
+        assert len(step.graphs) == 3
+        step()
+        torch.cuda.synchronize()
+        got_graph = grads(netG, netD)
+    print(f"[rank {rank}] graph form done", file=sys.stderr, flush=True)
     if SYNC_BN:      # synchronised statistics == the statistics of the concatenated batch: the running statistics agree too
         for k, v in want_stats.items():
             err = (got_stats[k] - v).abs().max().item() / max(v.abs().max().item(), 1e-6)
