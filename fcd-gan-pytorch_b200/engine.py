@@ -59,7 +59,8 @@ def set_sync_bn(enabled: bool, group=None) -> None:
     """Synchronised BatchNorm for data-parallel runs (no reference counterpart — the reference is single-device; SURVEY.md
     §8(e)): every train-mode BatchNorm call all-reduces its batch sums (2*C doubles forward, 2*C doubles backward) over
     `group`, so an N-rank run with equal shards computes exactly the statistics, running statistics and gradients of the
-    single-process run on the concatenated batch.  Off by default (per-rank statistics, the DDP default)."""
+    single-process run on the concatenated batch (tests/test_dp_gpu.py, 2 ranks on NCCL).  Off by default (per-rank
+    statistics, the DDP default).  Eager launches only: under CUDA-graph capture it raises."""
     import torch.distributed as dist
 
     if enabled and not dist.is_initialized():
@@ -76,6 +77,10 @@ def _sync_world() -> int:
 def _all_reduce_sum(t: torch.Tensor) -> None:
     import torch.distributed as dist
 
+    if _capturing():
+        # measured (round 2): SyncBN's all-reduces captured inside graph segments, mixed with the eager gradient all-reduces
+        # between the segments, hung on torch 2.11 / NCCL 2.28.9 — refuse instead of hanging a multi-GPU job
+        raise _lib.FcdError("set_sync_bn(True) is not supported under CUDA-graph capture: run SyncBN steps eagerly")
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_cfg["sync_bn"][0])
 
 

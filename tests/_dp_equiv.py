@@ -96,7 +96,7 @@ def main():
     got_stats = {k: v.clone() for n in (netG, netD) for k, v in n.state_dict().items() if "running" in k}
     print(f"[rank {rank}] eager exchange done", file=sys.stderr, flush=True)
     # N-rank sharded, CUDA graphs cut at the exchange points (eval-mode BatchNorm only: SyncBN's all-reduces inside captured
-    # segments mixed with eager all-reduces between them is not a validated combination — SyncBN runs are eager)
+    # segments mixed with eager all-reduces between them hung on this stack; the engine refuses SyncBN under capture)
     if SYNC_BN:
         got_graph = got_eager
     else:
