@@ -136,3 +136,51 @@ def test_raster_tile_grid_matches_the_oracle_geometry():
         assert (cover == 1).all()
     with pytest.raises(ValueError):
         TileGrid(100, 100, (20, 20), (10, 10))
+
+
+def test_usss_step_lean_equals_faithful_on_cpu_stand_ins():
+    """Host logic of steps.usss_gen: the faithful body back-propagates Loss (retain_graph) and then NetLoss = Loss + w*l1, which
+    hands G exactly 2 x dLoss and S only dNetLoss; the lean body does one sweep of NetLoss and doubles G's gradients.  Checked
+    here with plain torch stand-ins for the networks and the criterion (the step bodies only use the call surface), including the
+    order of the exchange points they yield."""
+    import torch
+    import torch.nn as nn
+
+    from fcdgan_b200 import steps as S
+
+    class Crit(nn.Module):
+        loss_perception = type("P", (), {"enabled": False})()
+
+        def forward(self, t, g, cmap):
+            m = 1 - cmap
+            gen = ((t - g).abs() * m).mean()
+            return gen, cmap.abs().mean(), torch.zeros(()), ((t * m - g * m) ** 2).mean()
+
+    class Seg(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(6, 1, 3, padding=1)
+
+        def forward(self, x, y):
+            return torch.sigmoid(self.c(torch.cat([x, y], 1)))
+
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(2, 3, 8, 8, generator=g), torch.randn(2, 3, 8, 8, generator=g)
+    seen = {}
+    for lean in (False, True):
+        torch.manual_seed(1)
+        netG, netS = nn.Conv2d(3, 3, 3, padding=1), Seg()
+        order = []
+
+        def hook(net, wait):
+            order.append((net is netG, wait))
+            seen[(lean, net is netG)] = [p.grad.clone() for p in net.parameters()]
+
+        out = S.usss_step(netG, netS, x, y, Crit(), ssim_weight=0.3, l1_weight=0.65, on_grads=hook, lean=lean)
+        assert order == [(True, False), (False, True)]            # G's bucket may stay in flight, S's is waited for
+        assert set(out) >= {"generator_loss", "l1_loss", "ssim_loss", "Loss", "NetLoss", "cmap"}
+    for is_g in (True, False):
+        for a, b in zip(seen[(True, is_g)], seen[(False, is_g)]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+    with __import__("pytest").raises(ValueError, match="perception_weight"):
+        S.usss_step(nn.Conv2d(3, 3, 1), Seg(), x, y, Crit(), perception_weight=0.4)
