@@ -176,6 +176,46 @@ __global__ void stage_pack4_kernel(const float* __restrict__ src, int C, int H, 
     st_split8(hi, lo, pix * 64 + g * 8, r);
 }
 
+// NCHW fp32 (N,C,H,W) -> split NHWC (N,H,W+M,Kp) with P horizontally adjacent pixels packed TIGHTLY into the channel axis:
+// dst[n,h,w'',j*C+c] = src[n,c,h,w''-M+j] for j < P (0 outside the image, 0 for k >= P*C).  With P = the filter width a whole
+// filter row of a KxK convolution over few bands is ONE tap: 9 x 13 = 117 -> K = 128 for the Generator's 9x9 layers
+// (Module.py:146,158) instead of 3 taps of 64 in the 4-pixel form (91 % instead of 61 % of the MMA work is useful).
+__global__ void stage_rowpack_kernel(const float* __restrict__ src, int C, int H, int W, int M, int P, int Kp,
+                                     __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    // block = 32 consecutive packed pixels of one row; the (32 + P - 1) source pixels x C channels they read go through
+    // shared memory (coalesced loads), then every (pixel, 8 consecutive k) slot is written as one 16-byte piece per plane
+    extern __shared__ float rp_tile[];                   // [C][TW] + k -> offset table
+    const int TW = ST_PIX + P - 1;
+    const int n = blockIdx.z, h = blockIdx.y, wq0 = blockIdx.x * ST_PIX;
+    const int Wp = W + M;
+    const long long HW = static_cast<long long>(H) * W;
+    const float* s = src + static_cast<long long>(n) * C * HW + static_cast<long long>(h) * W;
+    for (int e = threadIdx.x; e < C * TW; e += blockDim.x) {
+        const int c = e / TW, x = e - c * TW;
+        const int w = wq0 - M + x;
+        rp_tile[e] = (w >= 0 && w < W) ? __ldg(s + c * HW + w) : 0.f;
+    }
+    int* lut = reinterpret_cast<int*>(rp_tile + C * TW);
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        const int j = k / C, c = k - j * C;
+        lut[k] = j < P ? c * TW + j : -1;
+    }
+    __syncthreads();
+    const int kg = Kp / 8;
+    for (int slot = threadIdx.x; slot < ST_PIX * kg; slot += blockDim.x) {
+        const int i = slot / kg, k0 = (slot - i * kg) * 8;
+        if (wq0 + i >= Wp) continue;
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int off = lut[k0 + j];
+            r.v[j] = off >= 0 ? rp_tile[off + i] : 0.f;
+        }
+        const size_t pix = (static_cast<size_t>(n) * H + h) * Wp + wq0 + i;
+        st_split8(hi, lo, pix * Kp + k0, r);
+    }
+}
+
 // fp32 NHWC (pitch ld) -> NCHW fp32 (N,C,H,W); `accumulate` adds into dst.
 __global__ void unstage_kernel(const float* __restrict__ src, int ld, int C, long long HW, long long npix,
                                float* __restrict__ dst, int accumulate) {
@@ -812,6 +852,19 @@ int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, 
     FCD_CHECK_ARG(N <= 65535 && H <= 65535 && M <= 4, "fcd_stage_nchw_to_split_pack4: dims exceed the launch grid / margin > 4");
     stage_pack4_kernel<<<dim3((W + M + ST_PIX - 1) / ST_PIX, H, N), NT, 0, as_stream(stream)>>>(src, C, H, W, M, BF(dst_hi),
                                                                                               BF(dst_lo));
+    FCD_LAUNCH_OK();
+    return FCD_OK;
+}
+
+int fcd_stage_nchw_to_split_rowpack(const float* src, int N, int C, int H, int W, int M, int P, int Kp, void* dst_hi,
+                                    void* dst_lo, void* stream) {
+    FCD_CHECK_ARG(src && dst_hi && C >= 1 && P >= 1 && M >= 0, "fcd_stage_nchw_to_split_rowpack: bad arguments");
+    FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= P * C, "fcd_stage_nchw_to_split_rowpack: Kp must be a multiple of 8 and >= P*C");
+    FCD_CHECK_ARG(N <= 65535 && H <= 65535, "fcd_stage_nchw_to_split_rowpack: dims exceed the launch grid");
+    const size_t smem = sizeof(float) * C * (ST_PIX + P - 1) + sizeof(int) * Kp;
+    FCD_CHECK_ARG(smem <= 48 * 1024, "fcd_stage_nchw_to_split_rowpack: too many channels (%d) / pixels per pack (%d)", C, P);
+    stage_rowpack_kernel<<<dim3((W + M + ST_PIX - 1) / ST_PIX, H, N), NT, smem, as_stream(stream)>>>(src, C, H, W, M, P, Kp,
+                                                                                                    BF(dst_hi), BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

@@ -28,7 +28,8 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,...
 BN_MOMENTUM = 0.1
 
-_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1, "sync_bn": None}
+_cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1, "sync_bn": None,
+        "batch_branches": True, "rowpack": True}
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_g2.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
@@ -97,6 +98,21 @@ def set_im2col(on: bool) -> None:
     _cfg["im2col"] = bool(on)
 
 
+def batch_branches_enabled() -> bool:
+    """The Discriminator's two siamese branches run as one batch through the convolutions (modules.Discriminator_SRGAN_simple).
+    Off under SyncBN (its grouped BatchNorm form keeps per-rank statistics only)."""
+    return _cfg["batch_branches"] and _cfg["sync_bn"] is None
+
+
+def set_batch_branches(on: bool) -> None:
+    _cfg["batch_branches"] = bool(on)
+
+
+def set_rowpack(on: bool) -> None:
+    """Tight row-packed operand layout for the few-band 9x9 layers (row_pack_pixels); off = the 4-pixel form everywhere."""
+    _cfg["rowpack"] = bool(on)
+
+
 def set_engine(engine: int) -> None:
     _cfg["engine"] = engine
 
@@ -141,12 +157,13 @@ def pad_ch(c: int, tc: bool = True) -> int:
 class Act:
     """Split NHWC activation view (possibly a channel slice of a wider buffer)."""
 
-    __slots__ = ("hi", "lo", "N", "H", "W", "C", "Cp", "ld", "parent", "off", "_grad", "_ready", "name")
+    __slots__ = ("hi", "lo", "N", "H", "W", "C", "Cp", "ld", "parent", "off", "n0", "_grad", "_ready", "name")
 
-    def __init__(self, hi, lo, N, H, W, C, Cp, ld, parent=None, off=0, name=""):
+    def __init__(self, hi, lo, N, H, W, C, Cp, ld, parent=None, off=0, name="", n0=None):
         self.hi, self.lo = hi, lo
         self.N, self.H, self.W, self.C, self.Cp, self.ld = N, H, W, C, Cp, ld
         self.parent, self.off = parent, off
+        self.n0 = n0             # not None: a view of images [n0, n0 + N) of `parent` (batch_view)
         self._grad = None
         self._ready = False
         self.name = name
@@ -163,6 +180,12 @@ class Act:
         return Act(self.hi[..., off:off + C], None if self.lo is None else self.lo[..., off:off + C], self.N,
                    self.H, self.W, C, C, self.ld, parent=self, off=off, name=f"{self.name}[{off}:{off + C}]")
 
+    def batch_view(self, n0: int, n: int) -> "Act":
+        """Images [n0, n0 + n) of this activation (one siamese branch of a batch that carries both)."""
+        assert 0 <= n0 and n0 + n <= self.N
+        return Act(self.hi[n0:n0 + n], None if self.lo is None else self.lo[n0:n0 + n], n, self.H, self.W, self.C, self.Cp,
+                   self.ld, parent=self, off=0, name=f"{self.name}[n{n0}:{n0 + n}]", n0=n0)
+
     @property
     def npix(self) -> int:
         return self.N * self.H * self.W
@@ -178,7 +201,10 @@ class Act:
     def grad(self) -> torch.Tensor:
         if self._grad is None:
             if self.parent is not None:
-                self._grad = self.parent.grad[..., self.off:self.off + self.Cp]
+                g = self.parent.grad
+                if self.n0 is not None:
+                    g = g[self.n0:self.n0 + self.N]
+                self._grad = g[..., self.off:self.off + self.Cp]
             else:
                 self._grad = torch.empty((self.N, self.H, self.W, self.Cp), dtype=torch.float32, device=self.hi.device)
         return self._grad
@@ -198,7 +224,7 @@ class Act:
 class Z:
     """fp32 NHWC convolution output + BatchNorm statistics."""
 
-    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "stats", "sum_local", "dz", "pack_m", "bias_param", "db_done")
+    __slots__ = ("t", "N", "H", "W", "C", "Cp", "ld", "sum", "sqsum", "stats", "sum_local", "dz", "pack_m", "pack_p", "bias_param", "db_done")
 
     def __init__(self, t, N, H, W, C, Cp):
         self.t, self.N, self.H, self.W, self.C, self.Cp, self.ld = t, N, H, W, C, Cp, Cp
@@ -209,6 +235,7 @@ class Z:
         self.db_done = False
         self.dz: Optional[Act] = None
         self.pack_m = 0          # > 0: the producer wants its output gradient as a PackedAct with this left margin
+        self.pack_p = 4          # ... and this many pixels per pack (4: 16-slot form, else the tight row-packed form)
 
     @property
     def npix(self):
@@ -218,21 +245,37 @@ class Z:
 PACK_M = 4   # left margin (pixels) of a 4-pixel channel-packed tensor; must be >= the convolution padding
 
 
+def row_pack_pixels(C: int, KW: int) -> int:
+    """Pixels per pack for a KW-wide filter over a C-band image: KW (one tap of K = pad64(KW*C) per filter row, bands packed
+    tightly) when that needs fewer 64-channel K chunks per filter row than the 4-pixel form's ceil(KW/4) taps, else 4.
+    13 bands, 9x9 (Module.py:146,158): 117 -> 2 chunks instead of 3; 3 or 4 bands, 9x9: 1 instead of 3; 3x3 filters stay 4."""
+    if not _cfg["rowpack"]:
+        return 4
+    return KW if (KW * C + 63) // 64 < (KW + 3) // 4 and KW * C <= 256 else 4
+
+
 class PackedAct:
-    """Split NHWC tensor (N, H, W + M, 64) holding a <= 16-channel image with FOUR horizontally adjacent pixels packed
-    into the channel axis: v[n, h, w'', j*16 + c] = image[n, c, h, w'' - M + j]  (fcd_stage_nchw_to_split_pack4).
-    A K x K convolution over it needs ceil(K/4) taps of 64 channels per filter row instead of K taps."""
+    """Split NHWC tensor (N, H, W + M, Kp) holding a few-band image with P horizontally adjacent pixels packed into the
+    channel axis.  P = 4 (Kp = 64, <= 16 bands): v[n, h, w'', j*16 + c] = image[n, c, h, w'' - M + j]
+    (fcd_stage_nchw_to_split_pack4) — a K x K convolution over it needs ceil(K/4) taps of 64 channels per filter row instead
+    of K taps.  P != 4: bands packed tightly, v[n, h, w'', j*C + c] = image[n, c, h, w'' - M + j], j < P, Kp = pad64(P*C)
+    (fcd_stage_nchw_to_split_rowpack) — with P = K a whole filter row is one tap."""
 
-    __slots__ = ("hi", "lo", "N", "H", "W", "Wp", "C", "M")
+    __slots__ = ("hi", "lo", "N", "H", "W", "Wp", "C", "M", "P", "Kp")
 
-    def __init__(self, x_nchw: torch.Tensor, M: int = PACK_M):
+    def __init__(self, x_nchw: torch.Tensor, M: int = PACK_M, P: int = 4):
         N, C, H, W = x_nchw.shape
         assert C <= 16
-        self.N, self.C, self.H, self.W, self.M, self.Wp = N, C, H, W, M, W + M
-        self.hi = torch.empty((N, H, self.Wp, 64), dtype=torch.bfloat16, device=x_nchw.device)
+        self.N, self.C, self.H, self.W, self.M, self.Wp, self.P = N, C, H, W, M, W + M, P
+        self.Kp = 64 if P == 4 else pad_ch(P * C)
+        self.hi = torch.empty((N, H, self.Wp, self.Kp), dtype=torch.bfloat16, device=x_nchw.device)
         self.lo = torch.empty_like(self.hi) if _cfg["split"] else None
         x_nchw = x_nchw.contiguous()
-        _call("fcd_stage_nchw_to_split_pack4", x_nchw.data_ptr(), N, C, H, W, M, self.hi.data_ptr(), _lib.ptr(self.lo))
+        if P == 4:
+            _call("fcd_stage_nchw_to_split_pack4", x_nchw.data_ptr(), N, C, H, W, M, self.hi.data_ptr(), _lib.ptr(self.lo))
+        else:
+            _call("fcd_stage_nchw_to_split_rowpack", x_nchw.data_ptr(), N, C, H, W, M, P, self.Kp, self.hi.data_ptr(),
+                  _lib.ptr(self.lo))
 
     def p_hi(self):
         return self.hi.data_ptr()
@@ -347,6 +390,27 @@ def _w_unpack4_in(dwp: torch.Tensor, C: int, KW: int) -> torch.Tensor:
     """inverse of _w_pack4_in for a gradient: [Cout][64][KH][ng] -> [Cout][C][KH][KW]."""
     Cout, _, KH, ng = dwp.shape
     return dwp.view(Cout, 4, 16, KH, ng).permute(0, 2, 3, 4, 1).reshape(Cout, 16, KH, ng * 4)[:, :C, :, :KW]
+
+
+def _w_rowpack_in(w: torch.Tensor) -> torch.Tensor:
+    """[Cout][C][KH][KW] -> fake OIHW [Cout][pad64(KW*C)][KH][1] with W'[co][j*C+c][r][0] = w[co][c][r][j]."""
+    Cout, C, KH, KW = w.shape
+    wp = w.new_zeros((Cout, pad_ch(KW * C), KH, 1))
+    wp[:, :KW * C, :, 0] = w.permute(0, 3, 1, 2).reshape(Cout, KW * C, KH)
+    return wp
+
+
+def _w_unrowpack_in(dwp: torch.Tensor, C: int, KW: int) -> torch.Tensor:
+    """inverse of _w_rowpack_in for a gradient: [Cout][Kp][KH][1] -> [Cout][C][KH][KW]."""
+    Cout, _, KH, _ = dwp.shape
+    return dwp[:, :KW * C, :, 0].reshape(Cout, KW, C, KH).permute(0, 2, 3, 1)
+
+
+def _w_unrowpack_out(dwp: torch.Tensor, Cout: int, KW: int) -> torch.Tensor:
+    """Weight gradient taken against a row-packed OUTPUT gradient: T[j*Cout+co][ci][r][0] = dw[co][ci][r][KW-1-j]
+    -> [Cout][Cin][KH][KW]."""
+    _, Cin, KH, _ = dwp.shape
+    return dwp[:KW * Cout, :, :, 0].reshape(KW, Cout, Cin, KH).flip(0).permute(1, 2, 3, 0)
 
 
 def _w_pack4_out(w: torch.Tensor) -> torch.Tensor:
@@ -571,24 +635,27 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
 
 def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.Tensor], pad: int, stats: bool) -> Z:
     """Stride-1 convolution whose INPUT has <= 16 channels (Generator head Module.py:146, Segmentor first layer
-    Module.py:26), on a 4-pixel channel-packed input: ceil(KW/4) taps of K = 64 per filter row.  No input gradient
-    (the input is data)."""
+    Module.py:26), on a channel-packed input: ceil(KW/4) taps of K = 64 per filter row in the 4-pixel form, ONE tap of
+    K = pad64(KW*C) in the row-packed form (xp.P == KW).  No input gradient (the input is data)."""
     Cout, C, KH, KW = w.shape
     assert C == xp.C
-    ng, M, N = (KW + 3) // 4, xp.M, xp.N
-    assert pad <= M
+    M, N, Kp = xp.M, xp.N, xp.Kp
+    row = xp.P != 4
+    assert pad <= M and (not row or xp.P == KW)
+    ng, sstep = (1, 1) if row else ((KW + 3) // 4, 4)
     Cout_p = pad_ch(Cout)
     OH, OW = xp.H + 2 * pad - KH + 1, xp.W + 2 * pad - KW + 1
-    wf = _derived(w, "pack4_in", _w_pack4_in)
-    w_hi, w_lo = _packed(wf, Cout_p, 64, 0, "pack4_in")
+    form = "rowpack" if row else "pack4"
+    wf = _derived(w, form + "_in", _w_rowpack_in if row else _w_pack4_in)
+    w_hi, w_lo = _packed(wf, Cout_p, Kp, 0, form + "_in")
     bias = None if b is None else _padded_vec(b, Cout_p)
     zt = torch.empty((N, OH, OW, Cout_p), dtype=torch.float32, device=tape.device)
     z = Z(zt, N, OH, OW, Cout, Cout_p)
     flops = 2.0 * N * OH * OW * Cout * C * KH * KW
     shape = f"{KH}x{KW}s1 {C}->{Cout}"
-    _call("fcd_conv2d_taps_fwd", xp.p_hi(), xp.p_lo(), 64, xp.H, xp.Wp, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
-          zt.data_ptr(), z.ld, N, OH, OW, 64, Cout_p, KH, ng, -pad, 1, -pad + M, 4, 1, 1,
-          tag=f"conv_fwd_tc_pack4 {shape}", flops=flops)
+    _call("fcd_conv2d_taps_fwd", xp.p_hi(), xp.p_lo(), Kp, xp.H, xp.Wp, w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias), None, 0,
+          zt.data_ptr(), z.ld, N, OH, OW, Kp, Cout_p, KH, ng, -pad, 1, -pad + M, sstep, 1, 1,
+          tag=f"conv_fwd_tc_{form} {shape}", flops=flops)
     if stats:
         st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
         z.sum, z.sqsum, z.stats = st[0], st[1], st
@@ -603,16 +670,16 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
             z.dz = None
             return
         gw, acc = tape.pgrad(w)
-        dwp = torch.empty((Cout, 64, KH, ng), dtype=torch.float32, device=tape.device)
+        dwp = torch.empty((Cout, Kp, KH, ng), dtype=torch.float32, device=tape.device)
         need_db = b is not None and not z.db_done        # else: delivered by bn_act's backward (fcd_bn_bwd_finalize)
         z.db_done = False
         dbt = torch.empty((Cout,), dtype=torch.float32, device=tape.device) if need_db else None
-        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(64, Cout_p, KH, ng)
+        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(Kp, Cout_p, KH, ng)
         ws = _ws(tape.device, nbytes)
-        _call("fcd_conv2d_taps_wgrad", xp.p_hi(), xp.p_lo(), 64, xp.H, xp.Wp, dz.p_hi(), dz.p_lo(), dz.ld, OH, OW,
-              dwp.data_ptr(), _lib.ptr(dbt), N, 64, 64, Cout, Cout_p, KH, ng, -pad, -pad + M, 4, 0, ws.data_ptr(), nbytes,
-              tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
-        g = _w_unpack4_in(dwp, C, KW)
+        _call("fcd_conv2d_taps_wgrad", xp.p_hi(), xp.p_lo(), Kp, xp.H, xp.Wp, dz.p_hi(), dz.p_lo(), dz.ld, OH, OW,
+              dwp.data_ptr(), _lib.ptr(dbt), N, Kp, Kp, Cout, Cout_p, KH, ng, -pad, -pad + M, sstep, 0, ws.data_ptr(), nbytes,
+              tag=f"conv_wgrad_tc_{form} {shape}", flops=flops)
+        g = _w_unrowpack_in(dwp, C, KW) if row else _w_unpack4_in(dwp, C, KW)
         gw.add_(g) if acc else gw.copy_(g)
         if need_db:
             gb, accb = tape.pgrad(b)
@@ -627,16 +694,22 @@ def conv_im2col_s2(tape: Tape, x: torch.Tensor, w: torch.Tensor, b: Optional[tor
     """3x3 / stride 2 / pad 1 convolution of an NCHW DATA tensor with few channels (the first discriminator layer,
     Module.py:196: 13 -> 64): the staging kernel writes every output pixel's 3x3xC receptive field as one K = 9C row
     (padded to a multiple of 64), so forward and weight gradient are single 1x1 GEMMs over a quarter of the pixels
-    instead of 9 taps over a 64-channel zero-padded tensor.  No input gradient (callers use `conv` when x needs one)."""
+    instead of 9 taps over a 64-channel zero-padded tensor.  No input gradient (callers use `conv` when x needs one).
+    `x` may be a tuple of equally shaped tensors (the two siamese branches, Module.py:219-220): they become one batch."""
     Cout, C, KH, KW = w.shape
-    assert (KH, KW) == (3, 3) and x.shape[1] == C
-    N, _, H, W = x.shape
+    xs = tuple(x) if isinstance(x, (tuple, list)) else (x,)     # several tensors of one shape: staged into ONE batch
+    x = xs[0]
+    assert (KH, KW) == (3, 3) and all(t.shape == x.shape for t in xs) and x.shape[1] == C
+    Nx, _, H, W = x.shape
+    N = Nx * len(xs)
     OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     K = 9 * C
     Kp, Cout_p = pad_ch(K), pad_ch(Cout)
-    x = x.contiguous()
     a = tape.new_act(N, OH, OW, K, Cp=Kp, name="im2col")
-    _call("fcd_stage_im2col3x3s2", x.data_ptr(), N, C, H, W, a.p_hi(), a.p_lo(), Kp)
+    for i, t in enumerate(xs):
+        t = t.contiguous()
+        _call("fcd_stage_im2col3x3s2", t.data_ptr(), Nx, C, H, W, a.hi[i * Nx:].data_ptr(),
+              None if a.lo is None else a.lo[i * Nx:].data_ptr(), Kp)
     wf = _derived(w, "im2col", lambda t: t.permute(0, 2, 3, 1).reshape(Cout, K, 1, 1).contiguous())
     w_hi, w_lo = _packed(wf, Cout_p, Kp, 0, "im2col")
     bias = None if b is None else _padded_vec(b, Cout_p)
@@ -680,20 +753,23 @@ def conv_im2col_s2(tape: Tape, x: torch.Tensor, w: torch.Tensor, b: Optional[tor
 def conv_small_out(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, pad: int) -> Z:
     """Stride-1 convolution whose OUTPUT has <= 16 channels (Generator tail Module.py:158): the 64-wide N dimension
     of the MMA produces FOUR adjacent output pixels x 16 channel slots per row (TMA reads every 4th input pixel), the
-    output is a plain NHWC tensor with 16 channel slots; dgrad / wgrad run on the 4-pixel channel-packed output
-    gradient.  Requires OW % 4 == 0."""
+    output is a plain NHWC tensor with 16 channel slots; dgrad / wgrad run on the channel-packed output gradient (4-pixel
+    form, or the tight row-packed form when row_pack_pixels says so: one tap per filter row).  Requires OW % 4 == 0."""
     Cout, Cin, KH, KW = w.shape
     assert Cin == x.C and Cout <= 16
     N, H, W = x.N, x.H, x.W
     OH, OW = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
     assert OW % 4 == 0 and pad <= PACK_M
-    ng, M = (KW + 3) // 4, PACK_M
+    M = PACK_M
+    P = row_pack_pixels(Cout, KW)
+    if P != 4 and (KW - 1) - M - pad > 0:      # the row-packed weight gradient drops packed columns left of 0: fine only
+        P = 4                                  # while the x column they pair with is out of bounds too
     wq = _derived(w, "pack4_out", _w_pack4_out)
     w_hi, w_lo = _packed(wq, 64, x.Cp, 0, "pack4_out")
     bias = _derived(b, "pack4_bias", lambda t: torch.cat([_padded_vec(t, 16)] * 4))
     zt = torch.empty((N, OH, OW, 16), dtype=torch.float32, device=tape.device)
     z = Z(zt, N, OH, OW, Cout, 16)
-    z.pack_m = M
+    z.pack_m, z.pack_p = M, P
     flops = 2.0 * N * OH * OW * Cout * Cin * KH * KW
     shape = f"{KH}x{KW}s1 {Cin}->{Cout}"
     _call("fcd_conv2d_taps_fwd", x.p_hi(), x.p_lo(), x.ld, H, W, w_hi.data_ptr(), _lib.ptr(w_lo), bias.data_ptr(), None, 0,
@@ -702,29 +778,37 @@ def conv_small_out(tape: Tape, x: Act, w: torch.Tensor, b: torch.Tensor, pad: in
 
     def backward(tape):
         dzp = z.dz
-        assert isinstance(dzp, PackedAct), "conv_small_out backward: packed output gradient missing"
+        assert isinstance(dzp, PackedAct) and dzp.P == P, "conv_small_out backward: packed output gradient missing"
         dev = tape.device
         gw, acc = tape.pgrad(w)
         gb, accb = tape.pgrad(b)
-        # wgrad: T[(r,g)][ci][j*16+co] = sum x[oh+r-pad, ow''+4g+3-M-pad, ci] * dzp[oh, ow'', j*16+co] = dw[co][ci][r][4g+3-j]
-        dwp = torch.empty((64, Cin, KH, ng), dtype=torch.float32, device=dev)
-        db64 = torch.empty((64,), dtype=torch.float32, device=dev)
-        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(x.Cp, 64, KH, ng)
+        row = P != 4
+        Kp = dzp.Kp
+        ng, sstep = (1, 1) if row else ((KW + 3) // 4, 4)
+        form = "rowpack" if row else "pack4"
+        # wgrad, 4-pixel form: T[(r,g)][ci][j*16+co] = sum x[oh+r-pad, ow''+4g+3-M-pad, ci] * dzp[oh, ow'', j*16+co] = dw[co][ci][r][4g+3-j]
+        # row-packed form:     T[r][ci][j*Cout+co]   = sum x[oh+r-pad, ow''+KW-1-M-pad, ci] * dzp[oh, ow'', j*Cout+co] = dw[co][ci][r][KW-1-j]
+        dwp = torch.empty((Kp, Cin, KH, ng), dtype=torch.float32, device=dev)
+        dbk = torch.empty((Kp,), dtype=torch.float32, device=dev)
+        nbytes = _lib.load().fcd_conv2d_taps_wgrad_workspace(x.Cp, Kp, KH, ng)
         ws = _ws(dev, nbytes)
-        _call("fcd_conv2d_taps_wgrad", x.p_hi(), x.p_lo(), x.ld, H, W, dzp.p_hi(), dzp.p_lo(), 64, OH, dzp.Wp, dwp.data_ptr(),
-              db64.data_ptr(), N, Cin, x.Cp, 64, 64, KH, ng, -pad, 3 - M - pad, 4, 0, ws.data_ptr(), nbytes,
-              tag=f"conv_wgrad_tc_pack4 {shape}", flops=flops)
-        g = dwp.view(4, 16, Cin, KH, ng).flip(0).permute(1, 2, 3, 4, 0).reshape(16, Cin, KH, ng * 4)[:Cout, :, :, :KW]
+        _call("fcd_conv2d_taps_wgrad", x.p_hi(), x.p_lo(), x.ld, H, W, dzp.p_hi(), dzp.p_lo(), Kp, OH, dzp.Wp, dwp.data_ptr(),
+              dbk.data_ptr(), N, Cin, x.Cp, Kp, Kp, KH, ng, -pad, (KW - 1 if row else 3) - M - pad, sstep, 0, ws.data_ptr(), nbytes,
+              tag=f"conv_wgrad_tc_{form} {shape}", flops=flops)
+        if row:
+            g = _w_unrowpack_out(dwp, Cout, KW)
+        else:
+            g = dwp.view(4, 16, Cin, KH, ng).flip(0).permute(1, 2, 3, 4, 0).reshape(16, Cin, KH, ng * 4)[:Cout, :, :, :KW]
         gw.add_(g) if acc else gw.copy_(g)
-        gb.add_(db64[:Cout]) if accb else gb.copy_(db64[:Cout])
-        # dgrad: dx[h,w,ci] = sum_{r',g} dzp[h+r'-ph, w+4g-pw+M, :] . W''[ci][:][r'][g],  W'' = pack4_in(flip(w)^T)
-        wd = _derived(w, "pack4_dgrad", lambda t: _w_pack4_in(t.flip(2, 3).permute(1, 0, 2, 3)))
-        wd_hi, wd_lo = _packed(wd, x.Cp, 64, 0, "pack4_dgrad")
+        gb.add_(dbk[:Cout]) if accb else gb.copy_(dbk[:Cout])        # pack slot j = 0 sees every pixel once
+        # dgrad: dx[h,w,ci] = sum_{r',g} dzp[h+r'-ph, w+sstep*g-pw+M, :] . W''[ci][:][r'][g],  W'' = pack_in(flip(w)^T)
+        wd = _derived(w, form + "_dgrad", lambda t: (_w_rowpack_in if row else _w_pack4_in)(t.flip(2, 3).permute(1, 0, 2, 3)))
+        wd_hi, wd_lo = _packed(wd, x.Cp, Kp, 0, form + "_dgrad")
         gx = x.grad
         addend = gx.data_ptr() if x.ready else None
-        _call("fcd_conv2d_taps_fwd", dzp.p_hi(), dzp.p_lo(), 64, OH, dzp.Wp, wd_hi.data_ptr(), _lib.ptr(wd_lo), None, addend, x.ld,
-              gx.data_ptr(), x.ld, N, H, W, 64, x.Cp, KH, ng, -(KH - 1 - pad), 1, -(KW - 1 - pad) + M, 4, 1, 1,
-              tag=f"conv_dgrad_tc_pack4 {shape}", flops=flops)
+        _call("fcd_conv2d_taps_fwd", dzp.p_hi(), dzp.p_lo(), Kp, OH, dzp.Wp, wd_hi.data_ptr(), _lib.ptr(wd_lo), None, addend, x.ld,
+              gx.data_ptr(), x.ld, N, H, W, Kp, x.Cp, KH, ng, -(KH - 1 - pad), 1, -(KW - 1 - pad) + M, sstep, 1, 1,
+              tag=f"conv_dgrad_tc_{form} {shape}", flops=flops)
         x.mark_ready()
         z.dz = None
 
@@ -743,75 +827,98 @@ class BN:
 
 
 def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: Optional[torch.Tensor] = None,
-           slope_const: float = 0.0, residual: Optional[Act] = None, out: Optional[Act] = None) -> Act:
+           slope_const: float = 0.0, residual: Optional[Act] = None, out: Optional[Act] = None, groups: int = 1) -> Act:
     """[BatchNorm2d] -> activation -> [+ residual], written as a split activation (K6/K7).
-    BatchNorm statistics are those of THIS call (per siamese branch)."""
-    C, Cp, npix = z.C, z.Cp, z.npix
+    BatchNorm statistics are those of THIS call (per siamese branch).  `groups` > 1: the batch holds that
+    many equally sized calls of the reference back to back (the two branches of Module.py:219-220 run as one batch through
+    the convolutions); every group gets its own batch statistics, running-statistics update and backward sums, in call order."""
+    C, Cp, G = z.C, z.Cp, groups
+    assert z.N % G == 0
+    Ng, npix = z.N // G, z.npix // G          # images / pixels per statistics group
     dev = tape.device
+    if G > 1:
+        assert residual is None and out is None and _cfg["sync_bn"] is None, "bn_act: grouped form is plain BN + activation"
     if out is None:
         out = tape.new_act(z.N, z.H, z.W, C, Cp)
+    zp = [z.t[g * Ng:].data_ptr() for g in range(G)]
+    o_hi = [out.hi[g * Ng:].data_ptr() for g in range(G)]
+    o_lo = [None if out.lo is None else out.lo[g * Ng:].data_ptr() for g in range(G)]
     vec = None
+    gstats = None
     if bn is not None:
-        vec = torch.empty((6, Cp), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd, c1, c2
+        vec = torch.empty((G, 6, Cp), dtype=torch.float32, device=dev)  # per group: scale, shift, mean, invstd, c1, c2
         count = float(npix)
         if training:
-            assert z.sum is not None
-            if _cfg["sync_bn"] is not None and z.sum_local is None:      # statistics of the whole (all-rank) batch
-                z.sum_local = z.sum.clone()
-                _all_reduce_sum(z.stats)
-            count = float(npix) * _sync_world()
-        _call("fcd_bn_finalize", _lib.ptr(z.sum), _lib.ptr(z.sqsum), count, bn.weight.data_ptr(),
-              bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), C, Cp, BN_MOMENTUM, BN_EPS,
-              1 if training else 0, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr())
+            if G > 1:
+                gstats = torch.zeros((G, 2, Cp), dtype=torch.float64, device=dev)
+                for g in range(G):
+                    _call("fcd_bn_stats", zp[g], z.ld, npix, Cp, gstats[g, 0].data_ptr(), gstats[g, 1].data_ptr())
+            else:
+                assert z.sum is not None
+                if _cfg["sync_bn"] is not None and z.sum_local is None:      # statistics of the whole (all-rank) batch
+                    z.sum_local = z.sum.clone()
+                    _all_reduce_sum(z.stats)
+                count = float(npix) * _sync_world()
+        for g in range(G):
+            gsum, gsq = (gstats[g, 0], gstats[g, 1]) if gstats is not None else (z.sum, z.sqsum)
+            _call("fcd_bn_finalize", _lib.ptr(gsum), _lib.ptr(gsq), count, bn.weight.data_ptr(),
+                  bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), C, Cp, BN_MOMENTUM, BN_EPS,
+                  1 if training else 0, vec[g, 0].data_ptr(), vec[g, 1].data_ptr(), vec[g, 2].data_ptr(), vec[g, 3].data_ptr())
         if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            bn.num_batches_tracked.add_(G)
     sp = None if slope is None else slope.data_ptr()
-    _call("fcd_bn_act_fwd", z.t.data_ptr(), z.ld, None if vec is None else vec[0].data_ptr(),
-          None if vec is None else vec[1].data_ptr(), act, sp, slope_const,
-          None if residual is None else residual.p_hi(), None if residual is None else residual.p_lo(),
-          0 if residual is None else residual.ld, out.p_hi(), out.p_lo(), out.ld, npix, Cp)
+    for g in range(G):
+        _call("fcd_bn_act_fwd", zp[g], z.ld, None if vec is None else vec[g, 0].data_ptr(),
+              None if vec is None else vec[g, 1].data_ptr(), act, sp, slope_const,
+              None if residual is None else residual.p_hi(), None if residual is None else residual.p_lo(),
+              0 if residual is None else residual.ld, o_hi[g], o_lo[g], out.ld, npix, Cp)
 
     def backward(tape):
         assert out.ready, f"bn_act backward: gradient of {out.name} missing"
         da = out.grad
         dz = Act.empty(z.N, z.H, z.W, C, dev, Cp)
         need_reduce = bn is not None or act == ACT_PRELU
-        v = (lambda i: vec[i].data_ptr()) if vec is not None else (lambda i: None)
-        if need_reduce:
-            red = torch.zeros((2, Cp + 8), dtype=torch.float64, device=dev)
-            s1, s2, ds = red[0, :Cp], red[1, :Cp], red[0, Cp:]
-            _call("fcd_bn_act_bwd_reduce", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), act, sp,
-                  slope_const, npix, Cp, s1.data_ptr(), s2.data_ptr(), ds.data_ptr() if act == ACT_PRELU else None)
-            dgam = dbet = dsl = None
-            acc = 0
-            if bn is not None:
-                dgam, acc = tape.pgrad(bn.weight)
-                dbet, _ = tape.pgrad(bn.bias)
-            if act == ACT_PRELU:
-                dsl, acc_s = tape.pgrad(slope)
-                assert bn is None or acc_s == acc
-                acc = acc_s
-            c = vec if vec is not None else torch.empty((6, Cp), dtype=torch.float32, device=dev)
-            # the producing convolution's bias gradient (= per-channel sum of dz) comes out of the same sums in closed form
-            gb = acc_b = None
-            if z.bias_param is not None:
-                gb, acc_b = tape.pgrad(z.bias_param)
-                z.db_done = True
-            use_stats = bn is not None and training and z.sum is not None
-            zsum = z.sum
-            gl = None
-            if use_stats and z.sum_local is not None:        # SyncBN: dz needs the means over ALL ranks' batches
-                zsum = z.sum_local
-                gl = red[:, :Cp].contiguous()
-                _all_reduce_sum(gl)
-            _call("fcd_bn_bwd_finalize", s1.data_ptr(), s2.data_ptr(), float(npix), 1 if (training and bn is not None) else 0,
-                  C, Cp, c[4].data_ptr(), c[5].data_ptr(), _lib.ptr(dgam), _lib.ptr(dbet), acc,
-                  ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl),
-                  v(0), zsum.data_ptr() if use_stats else None, v(2) if use_stats else None, v(3) if use_stats else None,
-                  _lib.ptr(gb), acc_b or 0, None if gl is None else gl[0].data_ptr(), None if gl is None else gl[1].data_ptr(),
-                  float(npix) * _sync_world())
-        _call("fcd_bn_act_bwd_apply", da.data_ptr(), out.ld, z.t.data_ptr(), z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
-              sp, slope_const, dz.p_hi(), dz.p_lo(), dz.ld, npix, Cp)
+        red_all = torch.zeros((G, 2, Cp + 8), dtype=torch.float64, device=dev) if need_reduce else None
+        c_all = vec if vec is not None else (torch.empty((G, 6, Cp), dtype=torch.float32, device=dev) if need_reduce else None)
+        for g in range(G):
+            dap = da[g * Ng:].data_ptr()
+            v = (lambda i: vec[g, i].data_ptr()) if vec is not None else (lambda i: None)
+            if need_reduce:
+                red = red_all[g]
+                s1, s2, ds = red[0, :Cp], red[1, :Cp], red[0, Cp:]
+                _call("fcd_bn_act_bwd_reduce", dap, out.ld, zp[g], z.ld, v(0), v(1), v(2), v(3), act, sp,
+                      slope_const, npix, Cp, s1.data_ptr(), s2.data_ptr(), ds.data_ptr() if act == ACT_PRELU else None)
+                dgam = dbet = dsl = None
+                acc = 0
+                if bn is not None:
+                    dgam, acc = tape.pgrad(bn.weight)
+                    dbet, _ = tape.pgrad(bn.bias)
+                if act == ACT_PRELU:
+                    dsl, acc_s = tape.pgrad(slope)
+                    assert bn is None or acc_s == acc
+                    acc = acc_s
+                c = c_all[g]
+                # the producing convolution's bias gradient (= per-channel sum of dz) comes out of the same sums in closed form
+                gb = acc_b = None
+                if z.bias_param is not None:
+                    gb, acc_b = tape.pgrad(z.bias_param)
+                    z.db_done = True
+                gsum = gstats[g, 0] if gstats is not None else z.sum
+                use_stats = bn is not None and training and gsum is not None
+                zsum = gsum
+                gl = None
+                if use_stats and z.sum_local is not None:        # SyncBN: dz needs the means over ALL ranks' batches
+                    zsum = z.sum_local
+                    gl = red[:, :Cp].contiguous()
+                    _all_reduce_sum(gl)
+                _call("fcd_bn_bwd_finalize", s1.data_ptr(), s2.data_ptr(), float(npix), 1 if (training and bn is not None) else 0,
+                      C, Cp, c[4].data_ptr(), c[5].data_ptr(), _lib.ptr(dgam), _lib.ptr(dbet), acc,
+                      ds.data_ptr() if act == ACT_PRELU else None, _lib.ptr(dsl),
+                      v(0), zsum.data_ptr() if use_stats else None, v(2) if use_stats else None, v(3) if use_stats else None,
+                      _lib.ptr(gb), acc_b or 0, None if gl is None else gl[0].data_ptr(), None if gl is None else gl[1].data_ptr(),
+                      float(npix) * _sync_world())
+            _call("fcd_bn_act_bwd_apply", dap, out.ld, zp[g], z.ld, v(0), v(1), v(2), v(3), v(4), v(5), act,
+                  sp, slope_const, dz.hi[g * Ng:].data_ptr(), None if dz.lo is None else dz.lo[g * Ng:].data_ptr(), dz.ld, npix, Cp)
         z.dz = dz
         if DEBUG_CAPTURE is not None:
             DEBUG_CAPTURE.append(("da", da[..., :C].permute(0, 3, 1, 2).clone()))
@@ -819,7 +926,7 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
             DEBUG_CAPTURE.append(("dz", j[..., :C].permute(0, 3, 1, 2).clone()))
         if residual is not None:
             if residual.ready:
-                _call("fcd_add_f32", residual.grad.data_ptr(), residual.ld, da.data_ptr(), out.ld, npix, Cp)
+                _call("fcd_add_f32", residual.grad.data_ptr(), residual.ld, da.data_ptr(), out.ld, z.npix, Cp)
             elif residual.parent is None and out.parent is None:
                 residual._grad = da          # alias: `out.grad` is dead after this closure
                 residual.mark_ready()
@@ -1049,7 +1156,7 @@ def z_to_nchw(tape: Tape, z: Z, grad_slot: dict) -> torch.Tensor:
     def backward(tape):
         dout = grad_slot["dout"].contiguous()
         if z.pack_m:
-            z.dz = PackedAct(dout, z.pack_m)
+            z.dz = PackedAct(dout, z.pack_m, z.pack_p)
             return
         dz = Act.empty(z.N, z.H, z.W, z.C, tape.device, z.Cp)
         _call("fcd_stage_nchw_to_split", dout.data_ptr(), None, z.N, z.C, z.H, z.W, dz.p_hi(), dz.p_lo(), dz.ld, dz.Cp)

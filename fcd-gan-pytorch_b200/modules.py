@@ -303,7 +303,8 @@ class Generator(nn.Module):
             if self.n_channels <= 16 and not need[0]:
                 # 13-band head on the 4-pixel channel-packed input (3 taps of K = 64 per filter row instead of 9)
                 a = None
-                z = E.conv_small_in(tape, E.PackedAct(inputs[0]), self.block1[0].weight, self.block1[0].bias, 4, stats=False)
+                xp = E.PackedAct(inputs[0], P=E.row_pack_pixels(self.n_channels, 9))
+                z = E.conv_small_in(tape, xp, self.block1[0].weight, self.block1[0].bias, 4, stats=False)
             else:
                 a = E.stage_input(tape, inputs[0], need[0])
                 z = E.conv(tape, a, self.block1[0].weight, self.block1[0].bias, 1, 4, stats=False, x_needs_grad=need[0])
@@ -350,16 +351,19 @@ class Discriminator_SRGAN_simple(nn.Module):
         )
         self.sigmoid = nn.Sigmoid()
 
-    def _features(self, tape, a, training: bool, need_in: bool) -> E.Act:
+    def _features(self, tape, a, training: bool, need_in: bool, groups: int = 1) -> E.Act:
+        """The convolution stack of one branch (Module.py:196-210) — or, with `groups` = 2, of both branches as one batch
+        (x in the first half, y in the second): the convolutions, their data and weight gradients run once over 2B images,
+        BatchNorm keeps separate statistics per branch, in the reference's call order (x, then y)."""
         net = self.net
         if isinstance(a, E.Act):
             z = E.conv(tape, a, net[0].weight, net[0].bias, 2, 1, stats=False, x_needs_grad=need_in)
-        else:       # NCHW data tensor: receptive-field-packed first layer (no input gradient needed)
+        else:       # NCHW data tensor(s): receptive-field-packed first layer (no input gradient needed)
             z = E.conv_im2col_s2(tape, a, net[0].weight, net[0].bias)
         h = E.bn_act(tape, z, None, training, E.ACT_LEAKY, slope_const=0.2)
         for ci, bi in ((2, 3), (5, 6), (8, 9)):
-            z = E.conv(tape, h, net[ci].weight, net[ci].bias, 2, 1, stats=training)
-            h = E.bn_act(tape, z, _bn(net[bi]), training, E.ACT_LEAKY, slope_const=0.2)
+            z = E.conv(tape, h, net[ci].weight, net[ci].bias, 2, 1, stats=training and groups == 1)
+            h = E.bn_act(tape, z, _bn(net[bi]), training, E.ACT_LEAKY, slope_const=0.2, groups=groups)
         return h
 
     def forward(self, x, y):
@@ -373,12 +377,23 @@ class Discriminator_SRGAN_simple(nn.Module):
             # an input that needs no gradient (data, or masks built from a detached map) skips the 64-channel zero-padded
             # staging: its first layer runs on receptive-field-packed rows (engine.conv_im2col_s2)
             packed = [E.im2col_enabled() and not need[i] and 9 * self.n_channels <= 256 for i in range(2)]
+            c1, c3 = self.classifier[1], self.classifier[3]
+            slot = {}
+            B = inputs[0].shape[0]
+            if E.batch_branches_enabled() and packed[0] == packed[1] and need[0] == need[1]:
+                # both siamese branches as ONE batch of 2B images (x first): every convolution / gradient kernel launches once
+                # instead of twice, on twice the pixels (the small late layers fill whole waves of CTAs)
+                a2 = (inputs[0], inputs[1]) if packed[0] else E.stage_two_inputs(tape, inputs[0], inputs[1])
+                h = self._features(tape, a2, training, need[0], groups=2)
+                fx, fy = tape.track(h.batch_view(0, B)), tape.track(h.batch_view(B, B))
+                tape.push(lambda tape: h.mark_ready())      # runs right after the head's backward has filled both halves
+                out = E.disc_head(tape, fx, fy, c1.weight, c1.bias, c3.weight, c3.bias, slot)
+                acts = [None, None] if packed[0] else [E.BatchHalf(a2, 0, B), E.BatchHalf(a2, B, B)]
+                return out, slot, acts
             a = inputs[0] if packed[0] else E.stage_input(tape, inputs[0], need[0])
             b = inputs[1] if packed[1] else E.stage_input(tape, inputs[1], need[1])
             fx = self._features(tape, a, training, need[0])
             fy = self._features(tape, b, training, need[1])
-            c1, c3 = self.classifier[1], self.classifier[3]
-            slot = {}
             out = E.disc_head(tape, fx, fy, c1.weight, c1.bias, c3.weight, c3.bias, slot)
             return out, slot, [None if packed[0] else a, None if packed[1] else b]
 

@@ -123,6 +123,10 @@ int fcd_conv2d_taps_wgrad(const void* x_hi, const void* x_lo, int x_ld, int XH, 
                           size_t workspace_bytes, void* stream);
 /* NCHW fp32 (N, C <= 16, H, W) -> split NHWC (N, H, W+M, 64): dst[n,h,w'',j*16+c] = src[n,c,h,w''-M+j], j = 0..3. */
 int fcd_stage_nchw_to_split_pack4(const float* src, int N, int C, int H, int W, int M, void* dst_hi, void* dst_lo, void* stream);
+/* NCHW fp32 (N, C, H, W) -> split NHWC (N, H, W+M, Kp): dst[n,h,w'',j*C+c] = src[n,c,h,w''-M+j], j < P, zero for k >= P*C.
+ * P = the filter width makes a whole filter row ONE tap (9 pixels x 13 bands = 117 -> Kp = 128 for Module.py:146,158). */
+int fcd_stage_nchw_to_split_rowpack(const float* src, int N, int C, int H, int W, int M, int P, int Kp, void* dst_hi,
+                                    void* dst_lo, void* stream);
 
 /* ==== HBM-bound glue between the convolutions (elementwise.cu) =====================================
  * "split" outputs are conv operands (bf16 hi/lo planes); fp32 NHWC tensors are conv results / gradients. */

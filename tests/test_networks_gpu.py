@@ -117,8 +117,18 @@ def test_segmentor(name):
     _check_running(net, sd_ref)
 
 
+@pytest.fixture
+def branch_batching(request):
+    """Discriminator with its two siamese branches as one batch (the default) / as two passes."""
+    from fcdgan_b200 import engine as E
+    E.set_batch_branches(request.param)
+    yield request.param
+    E.set_batch_branches(True)
+
+
+@pytest.mark.parametrize("branch_batching", [True, False], indirect=True)
 @pytest.mark.parametrize("name", ["d13.pt", "d3_odd.pt"])
-def test_discriminator(name):
+def test_discriminator(name, branch_batching):
     fb.set_precision("parity")
     f = load_golden(name)
     net = _load(fb.Discriminator_SRGAN_simple(f["C"]), O.discriminator_spec(f["C"]), f["seed"])
@@ -158,8 +168,9 @@ def test_data_inputs_take_the_packed_13_band_path(kind, name):
     _check_running(net, sd_ref)
 
 
+@pytest.mark.parametrize("branch_batching", [True, False], indirect=True)
 @pytest.mark.parametrize("name", ["d13.pt", "d3_odd.pt"])
-def test_discriminator_data_inputs_take_the_im2col_path(name):
+def test_discriminator_data_inputs_take_the_im2col_path(name, branch_batching):
     """Inputs that need no gradient (data / masks from a detached map) run the first 3x3 stride-2 layer on receptive-field-
     packed rows (engine.conv_im2col_s2: one K = 9C GEMM); scores, parameter gradients and running statistics must match
     the reference all the same, in both precisions' code paths (parity checked against the golden values)."""
@@ -174,7 +185,9 @@ def test_discriminator_data_inputs_take_the_im2col_path(name):
         tags = [t[1] for t in E.PROFILE]
     finally:
         E.PROFILE = None
-    assert sum(t.startswith("conv_fwd_tc_im2col") for t in tags) == 2, tags
+    # both branches in one launch (engine.batch_branches_enabled) or one launch per branch
+    assert sum(t.startswith("conv_fwd_tc_im2col") for t in tags) == (1 if branch_batching else 2), tags
+    assert sum(t.startswith("conv_fwd_tc 3x3s2") for t in tags) == (3 if branch_batching else 6), tags
     assert rel_err(out, f["out"]) < OUT_TOL
     (out * f["r"].to(DEV)).sum().backward()
     _, _, grads, sd_ref = _oracle("discriminator", f)
@@ -183,6 +196,44 @@ def test_discriminator_data_inputs_take_the_im2col_path(name):
     with torch.no_grad():                                   # inference
         out2 = net.eval()(f["x"].to(DEV), f["y"].to(DEV))
     assert out2.shape == f["out"].shape and torch.isfinite(out2).all()
+
+
+@pytest.mark.parametrize("need_grad", [False, True])
+def test_discriminator_branches_as_one_batch_match_two_passes(need_grad):
+    """Module.py:219-220 runs the two siamese branches one after the other; the engine runs them as ONE batch of 2B images
+    through the convolutions with per-branch BatchNorm statistics (bn_act groups = 2).  Scores, input / parameter gradients
+    and running statistics must agree with the two-pass form to fp32 rounding (same per-pixel arithmetic, other split-K
+    partition of the weight gradients): 2e-5."""
+    from fcdgan_b200 import engine as E
+    fb.set_precision("parity")
+    torch.manual_seed(3)
+    B, C, H, W = 4, 13, 64, 48
+    x0, y0 = torch.randn(B, C, H, W, device=DEV), torch.randn(B, C, H, W, device=DEV)
+    r = torch.randn(B, device=DEV)
+    res = []
+    try:
+        for batched in (True, False):
+            E.set_batch_branches(batched)
+            torch.manual_seed(4)
+            net = fb.Discriminator_SRGAN_simple(C).to(DEV).train()
+            x, y = x0.clone().requires_grad_(need_grad), y0.clone().requires_grad_(need_grad)
+            out = net(x, y)
+            (out * r).sum().backward()
+            res.append((out.detach(), x.grad, y.grad, {k: p.grad.clone() for k, p in net.named_parameters()},
+                        {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}))
+    finally:
+        E.set_batch_branches(True)
+    (o1, dx1, dy1, g1, s1), (o2, dx2, dy2, g2, s2) = res
+    assert rel_err(o1, o2) < 2e-5
+    if need_grad:
+        assert rel_l2(dx1, dx2) < 2e-5 and rel_l2(dy1, dy2) < 2e-5
+    for k in g2:
+        if k in ("net.2.bias", "net.5.bias", "net.8.bias"):     # a conv bias in front of a train-mode BatchNorm: analytically
+            assert g1[k].abs().max() < 1e-6 and g2[k].abs().max() < 1e-6      # zero gradient, rounding noise in both forms
+            continue
+        assert rel_l2(g1[k], g2[k]) < 2e-5, k
+    for k in s2:
+        assert torch.allclose(s1[k].double(), s2[k].double(), rtol=1e-5, atol=1e-7), k
 
 
 def test_generator_double_backward_and_fast_mode():

@@ -385,17 +385,32 @@ def test_stage_roundtrip_and_mask():
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("C,Cout,K,pad,H,W", [(13, 64, 9, 4, 20, 24), (4, 64, 3, 1, 19, 21), (3, 64, 9, 4, 33, 40), (16, 128, 3, 1, 8, 8)])
-def test_conv_small_in_pack4(C, Cout, K, pad, H, W):
-    """<= 16-band input convolution on the 4-pixel channel-packed input (Generator head Module.py:146, Segmentor first
-    layer Module.py:26): forward, BN statistics, wgrad, db vs F.conv2d autograd in fp64.  Tolerance 3e-5."""
+@pytest.mark.parametrize("rowpack", [False, True])
+@pytest.mark.parametrize("C,Cout,K,pad,H,W", [(13, 64, 9, 4, 20, 24), (4, 64, 3, 1, 19, 21), (3, 64, 9, 4, 33, 40), (16, 128, 3, 1, 8, 8),
+                                              (13, 64, 9, 4, 9, 256), (4, 128, 9, 4, 21, 19)])
+def test_conv_small_in_pack4(C, Cout, K, pad, H, W, rowpack):
+    """<= 16-band input convolution on the channel-packed input (Generator head Module.py:146, Segmentor first
+    layer Module.py:26), 4-pixel form and tight row-packed form (one tap per filter row, engine.row_pack_pixels):
+    forward, BN statistics, wgrad, db vs F.conv2d autograd in fp64.  Tolerance 3e-5."""
     torch.manual_seed(9)
     N = 2
     x = torch.randn(N, C, H, W, device=DEV)
     w = (torch.randn(Cout, C, K, K, device=DEV) * 0.1).requires_grad_(True)
     b = torch.randn(Cout, device=DEV).requires_grad_(True)
     tape = E.Tape(DEV, True)
-    xp = E.PackedAct(x)
+    P = E.row_pack_pixels(C, K) if rowpack else 4
+    if rowpack and P == 4:
+        pytest.skip("the row-packed form does not apply to this shape (same launch as the 4-pixel case)")
+    xp = E.PackedAct(x, P=P)
+    # the staged operand itself: v[n, h, w'', j*cs + c] = x[n, c, h, w'' - M + j]
+    cs = 16 if P == 4 else C
+    v = joined(xp.hi, xp.lo)
+    want = torch.zeros_like(v)
+    xs = joined(*split(x))
+    for j in range(P):
+        lo_w, hi_w = max(0, xp.M - j), min(xp.Wp, W + xp.M - j)
+        want[:, :, lo_w:hi_w, j * cs:j * cs + C] = xs[:, :, :, lo_w - xp.M + j:hi_w - xp.M + j].permute(0, 2, 3, 1)
+    assert rel(v, want) < 1e-6 and bool((v[want == 0] == 0).all())
     z = E.conv_small_in(tape, xp, w, b, pad, stats=True)
     # reference on the bf16-pair-rounded operands
     xr = joined(*split(x))
@@ -413,10 +428,18 @@ def test_conv_small_in_pack4(C, Cout, K, pad, H, W):
     assert rel(tape.pgrads[id(w)], gw) < 3e-5 and rel(tape.pgrads[id(b)], gb) < 3e-5
 
 
-@pytest.mark.parametrize("Cin,Cout,K,pad,H,W", [(64, 13, 9, 4, 20, 24), (64, 4, 9, 4, 17, 32), (128, 3, 3, 1, 12, 8)])
-def test_conv_small_out_pack4(Cin, Cout, K, pad, H, W):
+@pytest.fixture
+def rowpack_switch(request):
+    E.set_rowpack(request.param)
+    yield request.param
+    E.set_rowpack(True)
+
+
+@pytest.mark.parametrize("rowpack_switch", [False, True], indirect=True)
+@pytest.mark.parametrize("Cin,Cout,K,pad,H,W", [(64, 13, 9, 4, 20, 24), (64, 4, 9, 4, 17, 32), (128, 3, 3, 1, 12, 8), (64, 13, 9, 4, 10, 256)])
+def test_conv_small_out_pack4(Cin, Cout, K, pad, H, W, rowpack_switch):
     """<= 16-channel output convolution (Generator tail Module.py:158): four output pixels per MMA row; dgrad and wgrad on
-    the 4-pixel channel-packed output gradient.  Tolerance 3e-5."""
+    the channel-packed output gradient (4-pixel form / tight row-packed form).  Tolerance 3e-5."""
     torch.manual_seed(10)
     N = 2
     x = torch.randn(N, Cin, H, W, device=DEV)
