@@ -12,6 +12,7 @@ namespace fcd {
 namespace {
 
 constexpr int NT = 256;
+constexpr long long IDX32_MAX = (1LL << 32) - 2 * NT;   // element counts below this index with 32-bit arithmetic
 
 struct F8 {
     float v[8];
@@ -104,13 +105,15 @@ __global__ void stage_kernel(const float* __restrict__ src, const float* __restr
 // receptive field: dst[n,oh,ow,(r*3+s)*C + c] = src[n,c,2*oh-1+r,2*ow-1+s] (0 outside the image, 0 for k >= 9*C).  The first
 // discriminator layer (Module.py:196, 13 -> 64 channels) then is ONE K = 128 GEMM over a quarter of the pixels instead of 9 taps
 // of a 64-channel zero-padded tensor (engine.py: conv_im2col_s2).  One thread = one (pixel, 8 consecutive k).
+template <int PIX>
 __global__ void stage_im2col_s2_kernel(const float* __restrict__ src, int C, int H, int W, int OH, int OW, int Kp,
                                        __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    // block = 32 consecutive output pixels of one output row: the 3 input rows x (2*32 + 1) pixels x C channels they read are
+    // block = PIX consecutive output pixels of one output row (128 where the row is long enough: the kernel is bound by the
+    // load -> barrier -> store round trip of a block, so more pixels per block = more bytes in flight): the 3 input rows x (2*32 + 1) pixels x C channels they read are
     // staged in shared memory with coalesced loads, then every (pixel, 8 consecutive k) slot is written as one 16-byte piece
     extern __shared__ float im_tile[];                 // [3][C][IM_W]
-    constexpr int IM_W = 2 * ST_PIX + 1;
-    const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * ST_PIX;
+    constexpr int IM_W = 2 * PIX + 1;
+    const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * PIX;
     const long long HW = static_cast<long long>(H) * W;
     const float* sn = src + static_cast<long long>(n) * C * HW;
     const int iw0 = 2 * ow0 - 1;
@@ -125,17 +128,35 @@ __global__ void stage_im2col_s2_kernel(const float* __restrict__ src, int C, int
             im_tile[rc * IM_W + x] = (row_in && iw >= 0 && iw < W) ? __ldg(line + iw) : 0.f;
         }
     }
-    // k -> offset of (tap row, channel, tap column) inside the staged tile (or -1 for the zero padding k >= 9*C): computed once
-    // per block instead of a division chain per element
-    int* lut = reinterpret_cast<int*>(im_tile + 3 * C * IM_W);
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    // k -> offset of (tap row, channel, tap column) inside the staged tile (or -1 for the zero padding k >= 9*C)
+    auto k_off = [&](int k) {
         const int tap = k / C, c = k - tap * C;
         const int tr = tap / 3, ts = tap - tr * 3;
-        lut[k] = tap < 9 ? (tr * C + c) * IM_W + ts : -1;
-    }
-    __syncthreads();
+        return tap < 9 ? (tr * C + c) * IM_W + ts : -1;
+    };
     const int kg = Kp / 8;
-    for (int slot = threadIdx.x; slot < ST_PIX * kg; slot += blockDim.x) {
+    if (blockDim.x % kg == 0) {
+        // every slot a thread visits has the same k group (the slot stride is a multiple of kg): its 8 offsets live in registers
+        // (a shared-memory table read with stride 8 is a 4-way bank conflict per element — measured 3x the HBM time)
+        const int k0 = (threadIdx.x % kg) * 8;
+        int off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) off[j] = k_off(k0 + j);
+        __syncthreads();
+        for (int i = threadIdx.x / kg; i < PIX; i += blockDim.x / kg) {
+            if (ow0 + i >= OW) break;
+            F8 r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r.v[j] = off[j] >= 0 ? im_tile[off[j] + 2 * i] : 0.f;
+            const size_t pix = (static_cast<size_t>(n) * OH + oh) * OW + ow0 + i;
+            st_split8(hi, lo, pix * Kp + k0, r);
+        }
+        return;
+    }
+    int* lut = reinterpret_cast<int*>(im_tile + 3 * C * IM_W);
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) lut[k] = k_off(k);
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < PIX * kg; slot += blockDim.x) {
         const int i = slot / kg, k0 = (slot - i * kg) * 8;
         if (ow0 + i >= OW) continue;
         F8 r;
@@ -180,13 +201,14 @@ __global__ void stage_pack4_kernel(const float* __restrict__ src, int C, int H, 
 // dst[n,h,w'',j*C+c] = src[n,c,h,w''-M+j] for j < P (0 outside the image, 0 for k >= P*C).  With P = the filter width a whole
 // filter row of a KxK convolution over few bands is ONE tap: 9 x 13 = 117 -> K = 128 for the Generator's 9x9 layers
 // (Module.py:146,158) instead of 3 taps of 64 in the 4-pixel form (91 % instead of 61 % of the MMA work is useful).
+template <int PIX>
 __global__ void stage_rowpack_kernel(const float* __restrict__ src, int C, int H, int W, int M, int P, int Kp,
                                      __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    // block = 32 consecutive packed pixels of one row; the (32 + P - 1) source pixels x C channels they read go through
+    // block = PIX consecutive packed pixels of one row (see stage_im2col_s2_kernel); the (PIX + P - 1) source pixels x C channels they read go through
     // shared memory (coalesced loads), then every (pixel, 8 consecutive k) slot is written as one 16-byte piece per plane
     extern __shared__ float rp_tile[];                   // [C][TW] + k -> offset table
-    const int TW = ST_PIX + P - 1;
-    const int n = blockIdx.z, h = blockIdx.y, wq0 = blockIdx.x * ST_PIX;
+    const int TW = (PIX + P - 1) | 1;                 // odd pitch: the channel lines start in different banks
+    const int n = blockIdx.z, h = blockIdx.y, wq0 = blockIdx.x * PIX;
     const int Wp = W + M;
     const long long HW = static_cast<long long>(H) * W;
     const float* s = src + static_cast<long long>(n) * C * HW + static_cast<long long>(h) * W;
@@ -195,14 +217,31 @@ __global__ void stage_rowpack_kernel(const float* __restrict__ src, int C, int H
         const int w = wq0 - M + x;
         rp_tile[e] = (w >= 0 && w < W) ? __ldg(s + c * HW + w) : 0.f;
     }
-    int* lut = reinterpret_cast<int*>(rp_tile + C * TW);
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    auto k_off = [&](int k) {
         const int j = k / C, c = k - j * C;
-        lut[k] = j < P ? c * TW + j : -1;
-    }
-    __syncthreads();
+        return j < P ? c * TW + j : -1;
+    };
     const int kg = Kp / 8;
-    for (int slot = threadIdx.x; slot < ST_PIX * kg; slot += blockDim.x) {
+    if (blockDim.x % kg == 0) {       // a thread keeps one k group: its 8 offsets live in registers (see stage_im2col_s2_kernel)
+        const int k0 = (threadIdx.x % kg) * 8;
+        int off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) off[j] = k_off(k0 + j);
+        __syncthreads();
+        for (int i = threadIdx.x / kg; i < PIX; i += blockDim.x / kg) {
+            if (wq0 + i >= Wp) break;
+            F8 r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r.v[j] = off[j] >= 0 ? rp_tile[off[j] + i] : 0.f;
+            const size_t pix = (static_cast<size_t>(n) * H + h) * Wp + wq0 + i;
+            st_split8(hi, lo, pix * Kp + k0, r);
+        }
+        return;
+    }
+    int* lut = reinterpret_cast<int*>(rp_tile + C * TW);
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) lut[k] = k_off(k);
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < PIX * kg; slot += blockDim.x) {
         const int i = slot / kg, k0 = (slot - i * kg) * 8;
         if (wq0 + i >= Wp) continue;
         F8 r;
@@ -497,12 +536,13 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ da, int da_ld,
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(2)  (floor: an odd last row / column is dropped)
 // ---------------------------------------------------------------------------------------------
+template <typename I>
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int in_ld, int N, int H, int W,
                                    int Cp, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld) {
     const int OH = H / 2, OW = W / 2, cg = Cp / 8;
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= 1LL * N * OH * OW * cg) return;
-    long long t = idx;
+    const I idx = static_cast<I>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (static_cast<long long>(idx) >= 1LL * N * OH * OW * cg) return;
+    I t = idx;
     const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
     const int ow = static_cast<int>(t % OW); t /= OW;
     const int oh = static_cast<int>(t % OH);
@@ -519,50 +559,67 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloat
     st_split8(out_hi, out_lo, ((static_cast<size_t>(n) * OH + oh) * OW + ow) * out_ld + c0, m);
 }
 
-// d_in[h,w] (+)= d_out[h/2,w/2] iff (h,w) is the first maximum of its window (torch keeps the first index)
+// d_in[h,w] (+)= d_out[h/2,w/2] iff (h,w) is the first maximum of its window (torch keeps the first index).
+// One thread = one 2x2 WINDOW x 8 channels: the four inputs and the output gradient are read once, the four input gradients
+// written once (the per-input-pixel form read every window four times: 2.8 TB/s of algorithmic bytes).  Pixels of an odd last
+// row / column belong to no window: gradient 0, written by the threads of the last window column / row.
+template <typename I>
 __global__ void maxpool_bwd_kernel(const float* __restrict__ d_out, int dout_ld, const __nv_bfloat16* in_hi,
                                    const __nv_bfloat16* in_lo, int in_ld, int N, int H, int W, int Cp, float* d_in,
                                    int din_ld, int accumulate) {
     const int OH = H / 2, OW = W / 2, cg = Cp / 8;
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= 1LL * N * H * W * cg) return;
-    long long t = idx;
+    const I idx = static_cast<I>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (static_cast<long long>(idx) >= 1LL * N * OH * OW * cg) return;
+    I t = idx;
     const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
-    const int w = static_cast<int>(t % W); t /= W;
-    const int h = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
-    float* dst = d_in + ((static_cast<size_t>(n) * H + h) * W + w) * din_ld + c0;
-    F8 g;
+    const int ow = static_cast<int>(t % OW); t /= OW;
+    const int oh = static_cast<int>(t % OH);
+    const int n = static_cast<int>(t / OH);
+    const size_t pix0 = (static_cast<size_t>(n) * H + 2 * oh) * W + 2 * ow;
+    const size_t poff[4] = {0, 1, static_cast<size_t>(W), static_cast<size_t>(W) + 1};
+    F8 m = ld_split8(in_hi, in_lo, pix0 * in_ld + c0);
+    int arg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
-    const int oh = h / 2, ow = w / 2;
-    if (oh < OH && ow < OW) {
-        const size_t base = ((static_cast<size_t>(n) * H + 2 * oh) * W + 2 * ow) * in_ld + c0;
-        const size_t offs[4] = {0, static_cast<size_t>(in_ld), static_cast<size_t>(W) * in_ld,
-                                static_cast<size_t>(W + 1) * in_ld};
-        const int me = (h & 1) * 2 + (w & 1);
-        F8 m = ld_split8(in_hi, in_lo, base);
-        int arg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 1; k < 4; ++k) {
+        const F8 v = ld_split8(in_hi, in_lo, (pix0 + poff[k]) * in_ld + c0);
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            const F8 v = ld_split8(in_hi, in_lo, base + offs[k]);
+        for (int j = 0; j < 8; ++j)
+            if (v.v[j] > m.v[j]) {
+                m.v[j] = v.v[j];
+                arg[j] = k;
+            }
+    }
+    const F8 go = ld_f32x8(d_out + ((static_cast<size_t>(n) * OH + oh) * OW + ow) * dout_ld + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (v.v[j] > m.v[j]) {
-                    m.v[j] = v.v[j];
-                    arg[j] = k;
-                }
+    for (int k = 0; k < 4; ++k) {
+        float* dst = d_in + (pix0 + poff[k]) * din_ld + c0;
+        F8 g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = (arg[j] == k) ? go.v[j] : 0.f;
+        if (accumulate) {
+            const F8 old = ld_f32x8(dst);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
         }
-        const F8 go = ld_f32x8(d_out + ((static_cast<size_t>(n) * OH + oh) * OW + ow) * dout_ld + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = (arg[j] == me) ? go.v[j] : 0.f;
+        st_f32x8(dst, g);
     }
-    if (accumulate) {
-        const F8 old = ld_f32x8(dst);
+    if (!accumulate) {       // the dropped odd row / column: zero gradient (accumulate: nothing to add)
+        F8 z;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
+        for (int j = 0; j < 8; ++j) z.v[j] = 0.f;
+        const bool last_w = (W & 1) && ow == OW - 1, last_h = (H & 1) && oh == OH - 1;
+        const size_t row0 = (static_cast<size_t>(n) * H + 2 * oh) * W;
+        if (last_w) {
+            st_f32x8(d_in + (row0 + W - 1) * din_ld + c0, z);
+            st_f32x8(d_in + (row0 + W + W - 1) * din_ld + c0, z);
+        }
+        if (last_h) {
+            const size_t rowl = (static_cast<size_t>(n) * H + H - 1) * W;
+            st_f32x8(d_in + (rowl + 2 * ow) * din_ld + c0, z);
+            st_f32x8(d_in + (rowl + 2 * ow + 1) * din_ld + c0, z);
+            if (last_w) st_f32x8(d_in + (rowl + W - 1) * din_ld + c0, z);
+        }
     }
-    st_f32x8(dst, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -576,13 +633,14 @@ __device__ __forceinline__ void src_coord(int o, float ratio, int in, int& i0, i
     l1 = f - i0;
 }
 
+template <typename I>
 __global__ void upsample_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int in_ld, int N, int h, int w,
                                     int Cp, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_ld, int H, int W,
                                     int pad_top, int pad_left) {
     const int cg = Cp / 8, uh = 2 * h, uw = 2 * w;
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= 1LL * N * H * W * cg) return;
-    long long t = idx;
+    const I idx = static_cast<I>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (static_cast<long long>(idx) >= 1LL * N * H * W * cg) return;
+    I t = idx;
     const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
     const int X = static_cast<int>(t % W); t /= W;
     const int Y = static_cast<int>(t % H);
@@ -612,12 +670,13 @@ __global__ void upsample_fwd_kernel(const __nv_bfloat16* in_hi, const __nv_bfloa
 }
 
 // gather form of the backward: every source pixel sums the (<= 6x6) destination pixels that read it
+template <typename I>
 __global__ void upsample_bwd_kernel(const float* __restrict__ d_out, int dout_ld, int N, int h, int w, int Cp, int H,
                                     int W, int pad_top, int pad_left, float* d_in, int din_ld) {
     const int cg = Cp / 8, uh = 2 * h, uw = 2 * w;
-    const long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    if (idx >= 1LL * N * h * w * cg) return;
-    long long t = idx;
+    const I idx = static_cast<I>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (static_cast<long long>(idx) >= 1LL * N * h * w * cg) return;
+    I t = idx;
     const int c0 = static_cast<int>(t % cg) * 8; t /= cg;
     const int x = static_cast<int>(t % w); t /= w;
     const int y = static_cast<int>(t % h);
@@ -839,10 +898,14 @@ int fcd_stage_im2col3x3s2(const float* src, int N, int C, int H, int W, void* ds
     FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= 9 * C, "fcd_stage_im2col3x3s2: Kp must be a multiple of 8 and >= 9*C");
     const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
     FCD_CHECK_ARG(N <= 65535 && OH <= 65535, "fcd_stage_im2col3x3s2: dims exceed the launch grid");
-    const size_t smem = sizeof(float) * 3 * C * (2 * ST_PIX + 1) + sizeof(int) * Kp;       // staged tile + k -> offset table
-    FCD_CHECK_ARG(smem <= 48 * 1024, "fcd_stage_im2col3x3s2: too many channels (%d)", C);
-    stage_im2col_s2_kernel<<<dim3((OW + ST_PIX - 1) / ST_PIX, OH, N), NT, smem, as_stream(stream)>>>(src, C, H, W, OH, OW, Kp,
-                                                                                                  BF(dst_hi), BF(dst_lo));
+    auto smem_for = [&](int pix) { return sizeof(float) * 3 * C * (2 * pix + 1) + sizeof(int) * Kp; };   // staged tile + k -> offset table
+    FCD_CHECK_ARG(smem_for(ST_PIX) <= 48 * 1024, "fcd_stage_im2col3x3s2: too many channels (%d)", C);
+    if (OW >= 128 && smem_for(128) <= 48 * 1024)
+        stage_im2col_s2_kernel<128><<<dim3((OW + 127) / 128, OH, N), NT, smem_for(128), as_stream(stream)>>>(
+            src, C, H, W, OH, OW, Kp, BF(dst_hi), BF(dst_lo));
+    else
+        stage_im2col_s2_kernel<ST_PIX><<<dim3((OW + ST_PIX - 1) / ST_PIX, OH, N), NT, smem_for(ST_PIX), as_stream(stream)>>>(
+            src, C, H, W, OH, OW, Kp, BF(dst_hi), BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -861,10 +924,14 @@ int fcd_stage_nchw_to_split_rowpack(const float* src, int N, int C, int H, int W
     FCD_CHECK_ARG(src && dst_hi && C >= 1 && P >= 1 && M >= 0, "fcd_stage_nchw_to_split_rowpack: bad arguments");
     FCD_CHECK_ARG(Kp % 8 == 0 && Kp >= P * C, "fcd_stage_nchw_to_split_rowpack: Kp must be a multiple of 8 and >= P*C");
     FCD_CHECK_ARG(N <= 65535 && H <= 65535, "fcd_stage_nchw_to_split_rowpack: dims exceed the launch grid");
-    const size_t smem = sizeof(float) * C * (ST_PIX + P - 1) + sizeof(int) * Kp;
-    FCD_CHECK_ARG(smem <= 48 * 1024, "fcd_stage_nchw_to_split_rowpack: too many channels (%d) / pixels per pack (%d)", C, P);
-    stage_rowpack_kernel<<<dim3((W + M + ST_PIX - 1) / ST_PIX, H, N), NT, smem, as_stream(stream)>>>(src, C, H, W, M, P, Kp,
-                                                                                                    BF(dst_hi), BF(dst_lo));
+    auto smem_for = [&](int pix) { return sizeof(float) * C * ((pix + P - 1) | 1) + sizeof(int) * Kp; };
+    FCD_CHECK_ARG(smem_for(ST_PIX) <= 48 * 1024, "fcd_stage_nchw_to_split_rowpack: too many channels (%d) / pixels per pack (%d)", C, P);
+    if (W + M >= 128 && smem_for(128) <= 48 * 1024)
+        stage_rowpack_kernel<128><<<dim3((W + M + 127) / 128, H, N), NT, smem_for(128), as_stream(stream)>>>(
+            src, C, H, W, M, P, Kp, BF(dst_hi), BF(dst_lo));
+    else
+        stage_rowpack_kernel<ST_PIX><<<dim3((W + M + ST_PIX - 1) / ST_PIX, H, N), NT, smem_for(ST_PIX), as_stream(stream)>>>(
+            src, C, H, W, M, P, Kp, BF(dst_hi), BF(dst_lo));
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -992,8 +1059,13 @@ int fcd_bn_act_bwd_apply(const float* da, int da_ld, const float* z, int z_ld, c
 int fcd_maxpool2_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int H, int W, int Cp, void* out_hi,
                      void* out_lo, int out_ld, void* stream) {
     FCD_CHECK_ARG(in_hi && out_hi && H >= 2 && W >= 2 && Cp % 8 == 0, "fcd_maxpool2_fwd: bad arguments");
-    maxpool_fwd_kernel<<<blocks_for(1LL * N * (H / 2) * (W / 2) * (Cp / 8)), NT, 0, as_stream(stream)>>>(
-        CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, BF(out_hi), BF(out_lo), out_ld);
+    const long long total = 1LL * N * (H / 2) * (W / 2) * (Cp / 8);
+    if (total < IDX32_MAX)     // 32-bit index arithmetic: a 64-bit division chain per thread costs more than its 64 bytes of traffic
+        maxpool_fwd_kernel<unsigned><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, BF(out_hi), BF(out_lo), out_ld);
+    else
+        maxpool_fwd_kernel<long long><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, BF(out_hi), BF(out_lo), out_ld);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -1001,8 +1073,14 @@ int fcd_maxpool2_fwd(const void* in_hi, const void* in_lo, int in_ld, int N, int
 int fcd_maxpool2_bwd(const float* d_out, int dout_ld, const void* in_hi, const void* in_lo, int in_ld, int N, int H,
                      int W, int Cp, float* d_in, int din_ld, int accumulate, void* stream) {
     FCD_CHECK_ARG(d_out && in_hi && d_in && Cp % 8 == 0, "fcd_maxpool2_bwd: bad arguments");
-    maxpool_bwd_kernel<<<blocks_for(1LL * N * H * W * (Cp / 8)), NT, 0, as_stream(stream)>>>(
-        d_out, dout_ld, CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, d_in, din_ld, accumulate);
+    FCD_CHECK_ARG(H >= 2 && W >= 2, "fcd_maxpool2_bwd: needs H, W >= 2");
+    const long long total = 1LL * N * (H / 2) * (W / 2) * (Cp / 8);
+    if (total < IDX32_MAX)
+        maxpool_bwd_kernel<unsigned><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            d_out, dout_ld, CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, d_in, din_ld, accumulate);
+    else
+        maxpool_bwd_kernel<long long><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            d_out, dout_ld, CBF(in_hi), CBF(in_lo), in_ld, N, H, W, Cp, d_in, din_ld, accumulate);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -1013,8 +1091,13 @@ int fcd_upsample2x_bilinear_fwd(const void* in_hi, const void* in_lo, int in_ld,
     FCD_CHECK_ARG(in_hi && out_hi && Cp % 8 == 0 && H >= 2 * h + pad_top && W >= 2 * w + pad_left && pad_top >= 0 &&
                       pad_left >= 0,
                   "fcd_upsample2x_bilinear_fwd: bad arguments");
-    upsample_fwd_kernel<<<blocks_for(1LL * N * H * W * (Cp / 8)), NT, 0, as_stream(stream)>>>(
-        CBF(in_hi), CBF(in_lo), in_ld, N, h, w, Cp, BF(out_hi), BF(out_lo), out_ld, H, W, pad_top, pad_left);
+    const long long total = 1LL * N * H * W * (Cp / 8);
+    if (total < IDX32_MAX)
+        upsample_fwd_kernel<unsigned><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            CBF(in_hi), CBF(in_lo), in_ld, N, h, w, Cp, BF(out_hi), BF(out_lo), out_ld, H, W, pad_top, pad_left);
+    else
+        upsample_fwd_kernel<long long><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            CBF(in_hi), CBF(in_lo), in_ld, N, h, w, Cp, BF(out_hi), BF(out_lo), out_ld, H, W, pad_top, pad_left);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }
@@ -1022,8 +1105,13 @@ int fcd_upsample2x_bilinear_fwd(const void* in_hi, const void* in_lo, int in_ld,
 int fcd_upsample2x_bilinear_bwd(const float* d_out, int dout_ld, int N, int h, int w, int Cp, int H, int W, int pad_top,
                                 int pad_left, float* d_in, int din_ld, void* stream) {
     FCD_CHECK_ARG(d_out && d_in && Cp % 8 == 0, "fcd_upsample2x_bilinear_bwd: bad arguments");
-    upsample_bwd_kernel<<<blocks_for(1LL * N * h * w * (Cp / 8)), NT, 0, as_stream(stream)>>>(
-        d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, d_in, din_ld);
+    const long long total = 1LL * N * h * w * (Cp / 8);
+    if (total < IDX32_MAX)
+        upsample_bwd_kernel<unsigned><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, d_in, din_ld);
+    else
+        upsample_bwd_kernel<long long><<<blocks_for(total), NT, 0, as_stream(stream)>>>(
+            d_out, dout_ld, N, h, w, Cp, H, W, pad_top, pad_left, d_in, din_ld);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

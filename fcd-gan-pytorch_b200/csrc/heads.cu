@@ -127,6 +127,126 @@ __global__ void outconv_bwd_kernel(const float* __restrict__ dout, const float* 
     }
 }
 
+// ---- OutConv, wide form: L = Cin / 8 lanes per pixel (16-byte loads of both planes), 32 / L pixels per warp pass -----------
+// The one-warp-per-pixel kernels above keep only Cin / 4 lanes busy and pay a 64-bit division per pixel; for the Segmentor's
+// Cin = 64 (Module.py:139) they ran at 1/8 of the HBM rate (r02 event tables: 0.59 ms forward, 1.45 ms backward at 32 x 256^2).
+__device__ __forceinline__ void ld_split8_regs(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float v[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(hi + off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+    if (lo) {
+        const uint4 ul = *reinterpret_cast<const uint4*>(lo + off);
+        const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(&ul);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(l[i]);
+            v[2 * i] += f.x;
+            v[2 * i + 1] += f.y;
+        }
+    }
+}
+
+template <int L>
+__global__ void outconv_fwd_wide_kernel(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int x_ld, int Cin,
+                                        const float* __restrict__ w, const float* __restrict__ b, int n_out, unsigned npix,
+                                        unsigned HW, float* __restrict__ out /* NCHW (N,n_out,H,W) */) {
+    constexpr int PPW = 32 / L;
+    const int lane = threadIdx.x & 31, sub = lane / L, l = lane % L;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    float wv[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[o][j] = o < n_out ? w[o * Cin + l * 8 + j] : 0.f;
+    for (unsigned p0 = warp * PPW; p0 < npix; p0 += nwarps * PPW) {
+        const unsigned pix = p0 + sub;
+        const bool valid = pix < npix;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) ld_split8_regs(x_hi, x_lo, static_cast<size_t>(pix) * x_ld + l * 8, v);
+        float acc[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a = fmaf(v[j], wv[o][j], a);
+#pragma unroll
+            for (int d = L / 2; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            acc[o] = a;
+        }
+        if (valid && l == 0) {
+            const unsigned n = pix / HW, p = pix - n * HW;
+            for (int o = 0; o < n_out; ++o) out[(static_cast<size_t>(n) * n_out + o) * HW + p] = sigmoidf_(acc[o] + b[o]);
+        }
+    }
+}
+
+template <int L>
+__global__ void outconv_bwd_wide_kernel(const float* __restrict__ dout, const float* __restrict__ out, const __nv_bfloat16* x_hi,
+                                        const __nv_bfloat16* x_lo, int x_ld, int Cin, const float* __restrict__ w, int n_out,
+                                        unsigned npix, unsigned HW, float* __restrict__ dx, int dx_ld, double* dw, double* db) {
+    constexpr int PPW = 32 / L;
+    const int lane = threadIdx.x & 31, sub = lane / L, l = lane % L;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int c = l * 8;
+    float wv[4][8], dwacc[4][8], dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            wv[o][j] = o < n_out ? w[o * Cin + c + j] : 0.f;
+            dwacc[o][j] = 0.f;
+        }
+    for (unsigned p0 = warp * PPW; p0 < npix; p0 += nwarps * PPW) {
+        const unsigned pix = p0 + sub;
+        if (pix >= npix) continue;
+        const unsigned n = pix / HW, p = pix - n * HW;
+        float dl[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int o = 0; o < n_out; ++o) {
+            const size_t i = (static_cast<size_t>(n) * n_out + o) * HW + p;
+            const float sg = out[i];
+            dl[o] = dout[i] * sg * (1.f - sg);
+        }
+        float v[8];
+        ld_split8_regs(x_hi, x_lo, static_cast<size_t>(pix) * x_ld + c, v);
+        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                g[j] = fmaf(dl[o], wv[o][j], g[j]);
+                dwacc[o][j] = fmaf(dl[o], v[j], dwacc[o][j]);
+            }
+        float* d = dx + static_cast<size_t>(pix) * dx_ld + c;
+        *reinterpret_cast<float4*>(d) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        if (l == 0)
+            for (int o = 0; o < n_out; ++o) dbacc[o] += dl[o];
+    }
+    // combine the block's partial sums in shared memory, then one double atomic per (o, c) and per o
+    __shared__ float red[4][128];
+    __shared__ float redb[4];
+    for (int t = threadIdx.x; t < 4 * 128; t += blockDim.x) red[t >> 7][t & 127] = 0.f;
+    if (threadIdx.x < 4) redb[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&red[o][c + j], dwacc[o][j]);
+    if (l == 0)
+        for (int o = 0; o < 4; ++o) atomicAdd(&redb[o], dbacc[o]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_out * Cin; t += blockDim.x) {
+        const int o = t / Cin, cc = t % Cin;
+        atomicAdd(dw + o * Cin + cc, static_cast<double>(red[o][cc]));
+    }
+    if (threadIdx.x < n_out) atomicAdd(db + threadIdx.x, static_cast<double>(redb[threadIdx.x]));
+}
+
 __global__ void double_to_float_kernel(const double* src, float* dst, int n, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (accumulate ? dst[i] : 0.f) + static_cast<float>(src[i]);
@@ -241,6 +361,26 @@ __global__ void mask_fwd_kernel(const float* __restrict__ a, const float* __rest
     }
     out[idx] = v * (1.f - m[n * HW + p]);
 }
+// The same on 4 consecutive pixels of one (n, c) plane per thread (float4 accesses, no 64-bit divisions): blockIdx.y = n*C + c.
+// Needs HW % 4 == 0 and 16-byte aligned tensors; the arithmetic per element is identical to mask_fwd_kernel's.
+__global__ void mask_fwd_vec4_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ region,
+                                     const float* __restrict__ m, int C, long long HW, float* __restrict__ out) {
+    const long long p = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) * 4;
+    if (p >= HW) return;
+    const int plane = blockIdx.y, n = plane / C;
+    const long long idx = plane * HW + p, pm = n * HW + p;
+    float4 v = *reinterpret_cast<const float4*>(a + idx);
+    if (region) {
+        const float4 r = *reinterpret_cast<const float4*>(region + pm);
+        const float4 w = *reinterpret_cast<const float4*>(b + idx);
+        v.x = v.x * (1.f - r.x) + w.x * r.x;
+        v.y = v.y * (1.f - r.y) + w.y * r.y;
+        v.z = v.z * (1.f - r.z) + w.z * r.z;
+        v.w = v.w * (1.f - r.w) + w.w * r.w;
+    }
+    const float4 k = *reinterpret_cast<const float4*>(m + pm);
+    *reinterpret_cast<float4*>(out + idx) = make_float4(v.x * (1.f - k.x), v.y * (1.f - k.y), v.z * (1.f - k.z), v.w * (1.f - k.w));
+}
 // dm[n,p] (+)= -sum_c dout * (a*(1-r)+b*r);   one thread per pixel
 __global__ void mask_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ region, int C, long long HW, long long npix,
@@ -274,6 +414,20 @@ int fcd_outconv_sigmoid_fwd(const void* x_hi, const void* x_lo, int x_ld, int Ci
     FCD_CHECK_ARG(x_hi && w && b && out_nchw, "fcd_outconv_sigmoid_fwd: null pointer");
     FCD_CHECK_ARG(n_out >= 1 && n_out <= 4 && Cin % 4 == 0 && x_ld % 4 == 0, "fcd_outconv_sigmoid_fwd: n_out in 1..4, Cin %% 4");
     const long long npix = 1LL * N * H * W;
+    const bool wide = (Cin == 32 || Cin == 64 || Cin == 128) && x_ld % 8 == 0 && npix < (1LL << 31) &&
+                      (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (!x_lo || (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0);
+    if (wide) {
+        const int L = Cin / 8, ppb = (NT / 32) * (32 / L);       // pixels per block pass
+        long long wb = (npix + ppb - 1) / ppb;
+        if (wb > 16LL * sm_count()) wb = 16LL * sm_count();
+        const unsigned g = static_cast<unsigned>(wb), np = static_cast<unsigned>(npix), hw = static_cast<unsigned>(1LL * H * W);
+        cudaStream_t st = as_stream(stream);
+        if (L == 4) outconv_fwd_wide_kernel<4><<<g, NT, 0, st>>>(CBF(x_hi), CBF(x_lo), x_ld, Cin, w, b, n_out, np, hw, out_nchw);
+        else if (L == 8) outconv_fwd_wide_kernel<8><<<g, NT, 0, st>>>(CBF(x_hi), CBF(x_lo), x_ld, Cin, w, b, n_out, np, hw, out_nchw);
+        else outconv_fwd_wide_kernel<16><<<g, NT, 0, st>>>(CBF(x_hi), CBF(x_lo), x_ld, Cin, w, b, n_out, np, hw, out_nchw);
+        FCD_LAUNCH_OK();
+        return FCD_OK;
+    }
     long long blocks = (npix + 7) / 8;
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     outconv_fwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, as_stream(stream)>>>(CBF(x_hi), CBF(x_lo), x_ld, Cin, w, b,
@@ -292,11 +446,26 @@ int fcd_outconv_sigmoid_bwd(const float* dout_nchw, const float* out_nchw, const
     cudaStream_t s = as_stream(stream);
     FCD_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * (n_out * Cin + n_out), s));
     const long long npix = 1LL * N * H * W;
-    long long blocks = (npix + 63) / 64;
-    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-    outconv_bwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w,
-                                                                    n_out, npix, 1LL * H * W, dx, dx_ld, scratch,
-                                                                    scratch + n_out * Cin);
+    const bool wide = (Cin == 32 || Cin == 64 || Cin == 128) && x_ld % 8 == 0 && npix < (1LL << 31) &&
+                      (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (!x_lo || (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0) &&
+                      (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
+    if (wide) {
+        const int L = Cin / 8, ppb = (NT / 32) * (32 / L);
+        long long wb = (npix + 8LL * ppb - 1) / (8LL * ppb);      // >= 8 pixels per thread before the block-level reduction
+        if (wb > 8LL * sm_count()) wb = 8LL * sm_count();
+        if (wb < 1) wb = 1;
+        const unsigned g = static_cast<unsigned>(wb), np = static_cast<unsigned>(npix), hw = static_cast<unsigned>(1LL * H * W);
+        double* sdb = scratch + n_out * Cin;
+        if (L == 4) outconv_bwd_wide_kernel<4><<<g, NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w, n_out, np, hw, dx, dx_ld, scratch, sdb);
+        else if (L == 8) outconv_bwd_wide_kernel<8><<<g, NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w, n_out, np, hw, dx, dx_ld, scratch, sdb);
+        else outconv_bwd_wide_kernel<16><<<g, NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w, n_out, np, hw, dx, dx_ld, scratch, sdb);
+    } else {
+        long long blocks = (npix + 63) / 64;
+        if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+        outconv_bwd_kernel<<<static_cast<unsigned>(blocks), NT, 0, s>>>(dout_nchw, out_nchw, CBF(x_hi), CBF(x_lo), x_ld, Cin, w,
+                                                                        n_out, npix, 1LL * H * W, dx, dx_ld, scratch,
+                                                                        scratch + n_out * Cin);
+    }
     FCD_LAUNCH_OK();
     double_to_float_kernel<<<(n_out * Cin + 127) / 128, 128, 0, s>>>(scratch, dw, n_out * Cin, accumulate);
     double_to_float_kernel<<<1, 32, 0, s>>>(scratch + n_out * Cin, db, n_out, accumulate);
@@ -347,8 +516,14 @@ int fcd_fc_bwd(const float* dout, const float* pre, const float* out, const floa
 int fcd_mask_fwd(const float* a, const float* b, const float* region, const float* mask, int N, int C, int H, int W,
                  float* out, void* stream) {
     FCD_CHECK_ARG(a && mask && out && ((region == nullptr) == (b == nullptr)), "fcd_mask_fwd: bad arguments");
-    const long long total = 1LL * N * C * H * W;
-    mask_fwd_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(a, b, region, mask, C, 1LL * H * W, total, out);
+    const long long total = 1LL * N * C * H * W, HW = 1LL * H * W;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (HW % 4 == 0 && 1LL * N * C <= 65535 && al16(a) && al16(mask) && al16(out) && al16(b) && al16(region)) {
+        mask_fwd_vec4_kernel<<<dim3(blocks_for(HW / 4), N * C), NT, 0, as_stream(stream)>>>(a, b, region, mask, C, HW, out);
+        FCD_LAUNCH_OK();
+        return FCD_OK;
+    }
+    mask_fwd_kernel<<<blocks_for(total), NT, 0, as_stream(stream)>>>(a, b, region, mask, C, HW, total, out);
     FCD_LAUNCH_OK();
     return FCD_OK;
 }

@@ -30,6 +30,15 @@ BN_MOMENTUM = 0.1
 
 _cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1, "sync_bn": None,
         "batch_branches": True, "rowpack": True}
+# A/B switches without code changes: FCD_ENGINE="rowpack=0,batch_branches=0" (bench.py reports the dictionary in its line)
+import os as _os
+
+for _item in filter(None, _os.environ.get("FCD_ENGINE", "").split(",")):
+    _k, _, _v = _item.partition("=")
+    if _k.strip() not in ("rowpack", "batch_branches", "im2col", "fuse_stats"):
+        raise ValueError(f"FCD_ENGINE: unknown switch {_k!r}")
+    _cfg[_k.strip()] = bool(int(_v or 1))
+
 DEBUG_CAPTURE = None  # set to a list to record (kind, tensor) pairs from the backward pass (scripts/dbg_g2.py)
 launch_count = 0     # number of libfcd_b200 kernels-launching calls (bench.py reports it)
 
@@ -314,8 +323,24 @@ def invalidate_weight_cache() -> None:
     """Public form of bump_weight_epoch().  The packed copies are keyed by (storage pointer, `Tensor._version`); writes
     that go through `.data` (`p.data.clamp_(-1, 1)` — the WGAN clip commented out at Demo_RSSS.py:308-309 —, `p.data.copy_`,
     EMA updates, `dist.broadcast(p.data)`) do NOT move the version counter, so call this after any such write.  Optimizer
-    steps, `load_state_dict`, `.to()` and in-place ops on the parameter itself are detected without it."""
+    steps (fused ones included, through torch's global post-step hook), `load_state_dict`, `.to()` and in-place ops on the
+    parameter itself are detected without it."""
     bump_weight_epoch()
+
+
+def _after_any_optimizer_step(*_args, **_kwargs) -> None:
+    bump_weight_epoch()
+
+
+# torch's fused optimizers (`torch.optim.Adam(fused=True)`, ...) update the parameters WITHOUT moving `Tensor._version`
+# (checked on torch 2.11: the version counter is the same before and after `step()`), so the (pointer, version) stamp of the
+# packed copies cannot see them: every optimizer step in the process invalidates the cache through torch's global post-step hook.
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+
+    _reg_post_hook(_after_any_optimizer_step)
+except ImportError:          # older torch: the stamp check alone (un-fused optimizers move the version counter)
+    pass
 
 
 def _capturing() -> bool:
@@ -458,10 +483,29 @@ class Tape:
                                                     # carries a gradient THROUGH the network): weight-gradient launches are skipped
         self.forked = False                         # work of this replay is in flight on the side stream
         self.held: List = []                        # buffers that work reads: kept alive until it has been joined
+        self._arena = None                          # zero-initialised float64 pool the accumulators are carved from (zeros64)
+        self._arena_used = 0
 
     def push(self, fn):
         if self.record:
             self.ops.append(fn)
+
+    ARENA = 1 << 16     # doubles per pool block (512 KB: every accumulator of a Segmentor pass; one fill instead of ~50)
+
+    def zeros64(self, *shape) -> torch.Tensor:
+        """Zero-initialised float64 tensor for a kernel's atomics / sums (BatchNorm statistics, backward reductions), carved
+        from a pool that is filled once per block: a pass needed one tiny fill kernel per convolution and per BatchNorm
+        backward.  Slices are never handed out twice (a replayed tape gets fresh zeros), 16-byte aligned."""
+        n = 1
+        for d in shape:
+            n *= d
+        n_al = (n + 1) // 2 * 2
+        if self._arena is None or self._arena_used + n_al > self._arena.numel():
+            self._arena = torch.zeros(max(self.ARENA, n_al), dtype=torch.float64, device=self.device)
+            self._arena_used = 0
+        v = self._arena[self._arena_used:self._arena_used + n].view(shape)
+        self._arena_used += n_al
+        return v
 
     def track(self, a: Act) -> Act:
         if self.record:
@@ -573,7 +617,7 @@ def conv(tape: Tape, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], stride:
     z = Z(zt, N, OH, OW, Cout, Cout_p)
     fuse = stats and _cfg["fuse_stats"]
     if stats:
-        st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
+        st = tape.zeros64(2, Cout_p)
         z.sum, z.sqsum, z.stats = st[0], st[1], st
     eng = _conv_engine_name(Cin_p, Cout_p, KH, KW, stride)
     flops = 2.0 * N * OH * OW * Cout * Cin * KH * KW          # algorithmic (un-padded) multiply-adds x 2
@@ -657,7 +701,7 @@ def conv_small_in(tape: Tape, xp: PackedAct, w: torch.Tensor, b: Optional[torch.
           zt.data_ptr(), z.ld, N, OH, OW, Kp, Cout_p, KH, ng, -pad, 1, -pad + M, sstep, 1, 1,
           tag=f"conv_fwd_tc_{form} {shape}", flops=flops)
     if stats:
-        st = torch.zeros((2, Cout_p), dtype=torch.float64, device=tape.device)
+        st = tape.zeros64(2, Cout_p)
         z.sum, z.sqsum, z.stats = st[0], st[1], st
         _call("fcd_bn_stats", zt.data_ptr(), z.ld, z.npix, Cout_p, z.sum.data_ptr(), z.sqsum.data_ptr())
     z.bias_param = b
@@ -850,7 +894,7 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
         count = float(npix)
         if training:
             if G > 1:
-                gstats = torch.zeros((G, 2, Cp), dtype=torch.float64, device=dev)
+                gstats = tape.zeros64(G, 2, Cp)
                 for g in range(G):
                     _call("fcd_bn_stats", zp[g], z.ld, npix, Cp, gstats[g, 0].data_ptr(), gstats[g, 1].data_ptr())
             else:
@@ -878,7 +922,7 @@ def bn_act(tape: Tape, z: Z, bn: Optional[BN], training: bool, act: int, slope: 
         da = out.grad
         dz = Act.empty(z.N, z.H, z.W, C, dev, Cp)
         need_reduce = bn is not None or act == ACT_PRELU
-        red_all = torch.zeros((G, 2, Cp + 8), dtype=torch.float64, device=dev) if need_reduce else None
+        red_all = tape.zeros64(G, 2, Cp + 8) if need_reduce else None
         c_all = vec if vec is not None else (torch.empty((G, 6, Cp), dtype=torch.float32, device=dev) if need_reduce else None)
         for g in range(G):
             dap = da[g * Ng:].data_ptr()

@@ -184,3 +184,17 @@ def test_usss_step_lean_equals_faithful_on_cpu_stand_ins():
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
     with __import__("pytest").raises(ValueError, match="perception_weight"):
         S.usss_step(nn.Conv2d(3, 3, 1), Seg(), x, y, Crit(), perception_weight=0.4)
+
+
+def test_any_optimizer_step_invalidates_the_packed_weight_cache():
+    """Fused optimizers do not move Tensor._version, so the engine's cache stamp also carries an epoch that torch's global
+    optimizer post-step hook bumps (engine._after_any_optimizer_step)."""
+    import torch
+    from fcdgan_b200 import engine as E
+    m = torch.nn.Linear(4, 4)
+    for kw in ({}, {"fused": True}):
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, **kw)
+        m(torch.randn(2, 4)).sum().backward()
+        e0 = E._weight_epoch
+        opt.step()
+        assert E._weight_epoch > e0

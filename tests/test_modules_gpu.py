@@ -148,3 +148,23 @@ def test_weight_cache_follows_data_writes_after_invalidate():
         y2 = fresh(x)
     assert not torch.allclose(y0, y1)
     assert torch.equal(y1, y2)
+
+
+def test_weight_cache_follows_fused_optimizer_steps():
+    """torch's fused optimizers update parameters without moving Tensor._version; the engine invalidates its packed conv weights
+    after every optimizer step (global post-step hook), so an eager training loop with `Adam(fused=True)` sees its own updates."""
+    fb.set_precision("parity")
+    torch.manual_seed(0)
+    net = fb.Generator(4).to(DEV).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2, fused=True)
+    x = torch.randn(2, 4, 40, 36, device=DEV)
+    net(x).square().mean().backward()
+    v0 = net.block2.conv1.weight._version
+    opt.step()
+    assert net.block2.conv1.weight._version == v0, "torch changed: fused Adam now moves the version counter (hook still harmless)"
+    with torch.no_grad():
+        y1 = net.eval()(x)
+        fresh = fb.Generator(4).to(DEV).eval()
+        fresh.load_state_dict(net.state_dict())
+        y2 = fresh(x)
+    assert torch.equal(y1, y2)

@@ -245,12 +245,15 @@ def test_bn_act_fwd_bwd(act, use_bn, training, residual):
         assert res.ready and rel(res.grad.permute(0, 3, 1, 2), grads[k]) < 1e-6
 
 
-@pytest.mark.parametrize("H,W", [(16, 16), (11, 9), (27, 55)])
-def test_maxpool(H, W):
-    """nn.MaxPool2d(2) floor semantics + first-max gradient routing (Module.py:44); exact (selection only)."""
+@pytest.mark.parametrize("accumulate", [False, True])
+@pytest.mark.parametrize("H,W", [(16, 16), (11, 9), (27, 55), (8, 13), (5, 2)])
+def test_maxpool(H, W, accumulate):
+    """nn.MaxPool2d(2) floor semantics + first-max gradient routing (Module.py:44); exact (selection only).  The gradient is
+    written (pixels of a dropped odd row / column get 0) or added to one that is already there (the skip connection's)."""
     torch.manual_seed(3)
     N, C = 2, 64
     x = torch.randn(N, C, H, W, device=DEV)
+    x[0, :, 0:2, 0:2] = 1.5          # ties inside a window: torch routes the gradient to the first maximum
     tape = E.Tape(DEV, True)
     a = tape.track(act_from(x))
     out = E.maxpool2(tape, a)
@@ -260,9 +263,17 @@ def test_maxpool(H, W):
     d = torch.randn_like(ref)
     out.grad.copy_(d.permute(0, 2, 3, 1).float())
     out.mark_ready()
+    pre = torch.randn(N, H, W, a.Cp, device=DEV)
+    if accumulate:
+        a.grad.copy_(pre)
+        a.mark_ready()
+    else:
+        a.grad.fill_(float("nan"))   # every element must be written
     tape.ops[-1](tape)
     (gx,) = torch.autograd.grad(ref, xr, d)
-    assert rel(a.grad.permute(0, 3, 1, 2), gx) < 1e-6
+    if accumulate:
+        gx = gx + pre[..., :C].permute(0, 3, 1, 2).double()
+    assert rel(a.grad[..., :C].permute(0, 3, 1, 2), gx) < 1e-6
 
 
 @pytest.mark.parametrize("h,w,H,W", [(8, 8, 16, 16), (13, 5, 27, 11), (12, 12, 25, 25), (1, 2, 2, 4)])
