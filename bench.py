@@ -528,7 +528,9 @@ def run_ours(args):
                                         "algorithmic minimum SURVEY.md 8(d) counts)" if args.form == "lean" else
                                         "faithful: the reference's call sequence, call for call (its dead backward sweeps included)"),
                           "l2": "per-step working set (>20 GB) >> 126 MB L2; no flush needed",
-                          "algorithmic_gflop_per_unit": cfg["gf"], "peak_mem_GiB": round(peak_mem, 1)},
+                          "algorithmic_gflop_per_unit": cfg["gf"], "peak_mem_GiB": round(peak_mem, 1),
+                          "engine": {k: fb.engine._cfg[k] for k in ("rowpack", "batch_branches", "im2col", "fuse_stats")},
+                          "optimizer": "torch.optim.Adam(fused=True) / RMSprop (foreach), capturable"},
                "clocks": clocks,
                "e2e": {"value": round(e2e_value, 2), "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * n_loss},
                "gpu_launches": launches, "gpu_launches_note": "libfcd_b200 C-ABI calls in the timed region (each launches >= 1 kernel)",

@@ -12,6 +12,7 @@ try:
     d=json.loads(open('$1').read()); gb=d.get('gpu_baseline') or {}
     print(d['value'], d['unit'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['step_frac_of_peak'], 'dom', d['roofline']['kernel'], d['roofline']['frac'], 'cudnn', (gb.get('tf32') or {}).get('value'), (gb.get('fp32') or {}).get('value'), 'B', gb.get('batch'), 'cpu', (d.get('cpu_baseline') or {}).get('value'), 'loss_check', (d.get('loss_check') or {}).get('ok'))
 except Exception as e: print('no json', e)"; }
+timeout 300 python scripts/bench_small_kernels.py 16 > gpurun_out/v_small_kernels.log 2>&1; tail -n 14 gpurun_out/v_small_kernels.log
 for cfg in 2 g32 4 5 3; do
   extra="--no-cpu-baseline"; [ "$cfg" = "2" ] && extra=""
   timeout -s KILL 900 python bench.py --config $cfg --steps 10 --warmup 3 $extra --profile-out gpurun_out/v_table_$cfg.txt \

