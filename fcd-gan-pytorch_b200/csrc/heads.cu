@@ -227,24 +227,40 @@ __global__ void outconv_bwd_wide_kernel(const float* __restrict__ dout, const fl
         if (l == 0)
             for (int o = 0; o < n_out; ++o) dbacc[o] += dl[o];
     }
-    // combine the block's partial sums in shared memory, then one double atomic per (o, c) and per o
-    __shared__ float red[4][128];
-    __shared__ float redb[4];
-    for (int t = threadIdx.x; t < 4 * 128; t += blockDim.x) red[t >> 7][t & 127] = 0.f;
-    if (threadIdx.x < 4) redb[threadIdx.x] = 0.f;
-    __syncthreads();
+    // deterministic combination: the 32 / L pixel sub-groups of a warp by shuffles, the 8 warps of the block in shared memory in
+    // a fixed order, then one double atomic per (o, c) and per o
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
+    for (int o = 0; o < 4; ++o) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&red[o][c + j], dwacc[o][j]);
-    if (l == 0)
-        for (int o = 0; o < 4; ++o) atomicAdd(&redb[o], dbacc[o]);
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int d = L; d < 32; d <<= 1) dwacc[o][j] += __shfl_xor_sync(0xffffffffu, dwacc[o][j], d);
+#pragma unroll
+        for (int d = L; d < 32; d <<= 1) dbacc[o] += __shfl_xor_sync(0xffffffffu, dbacc[o], d);
+    }
+    __shared__ float red[8][4][128];
+    __shared__ float redb[8][4];
+    const int wid = threadIdx.x >> 5;
+    if (sub == 0) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[wid][o][c + j] = dwacc[o][j];
+        if (l == 0)
+            for (int o = 0; o < 4; ++o) redb[wid][o] = dbacc[o];
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < n_out * Cin; t += blockDim.x) {
         const int o = t / Cin, cc = t % Cin;
-        atomicAdd(dw + o * Cin + cc, static_cast<double>(red[o][cc]));
+        float sum = 0.f;
+        for (int k = 0; k < 8; ++k) sum += red[k][o][cc];
+        atomicAdd(dw + o * Cin + cc, static_cast<double>(sum));
     }
-    if (threadIdx.x < n_out) atomicAdd(db + threadIdx.x, static_cast<double>(redb[threadIdx.x]));
+    if (threadIdx.x < n_out) {
+        float sum = 0.f;
+        for (int k = 0; k < 8; ++k) sum += redb[k][threadIdx.x];
+        atomicAdd(db + threadIdx.x, static_cast<double>(sum));
+    }
 }
 
 __global__ void double_to_float_kernel(const double* src, float* dst, int n, int accumulate) {

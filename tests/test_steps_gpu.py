@@ -186,26 +186,50 @@ def _exchange_grads(step, *args, **kw):
 _ZERO_GRAD = re.compile(r".*double_conv\.[03]\.bias|block[2-6]\.conv[12]\.bias|block7\.0\.bias|net\.[258]\.bias")
 
 
-def _same_grads(a, b, what):
+def _same_grads(a, b, what, tol=2e-4, l2=False):
+    """Every gradient tensor of `a` equals its counterpart in `b`: element-wise (max |diff| over the tensor's largest element) or,
+    with `l2`, in the relative L2 norm (a handful of elements may differ a lot: activation-kink flips, see the test)."""
     assert a.keys() == b.keys(), what
     gmax = max(float(v.abs().max()) for v in b.values())
+    nmax = max(float(v.norm()) for v in b.values())
     for k in b:
         if _ZERO_GRAD.fullmatch(k):
             assert float(a[k].abs().max()) < 1e-3 * gmax, f"{what}: {k} should be ~0"
             continue
-        scale = max(float(b[k].abs().max()), 1e-3 * gmax)
-        err = float((a[k] - b[k]).abs().max()) / scale
-        # fp32 atomics of the weight-gradient reductions (run-to-run noise) + the rounding of D's two first-layer code paths
-        # (packed rows when its inputs carry no gradient, zero-padded otherwise); a skipped or doubled sweep would show as O(1)
-        assert err < 2e-4, f"{what}: {k} differs by {err:.3g}"
+        if l2:
+            err = float((a[k] - b[k]).norm()) / max(float(b[k].norm()), 1e-3 * nmax)
+        else:
+            err = float((a[k] - b[k]).abs().max()) / max(float(b[k].abs().max()), 1e-3 * gmax)
+        # fp32 atomics of the weight-gradient reductions (run-to-run noise); a skipped or doubled sweep would show as O(1)
+        assert err < tol, f"{what}: {k} differs by {err:.3g}"
 
 
+@pytest.fixture
+def d_first_layer_form(request):
+    """Discriminator first layer: receptive-field-packed rows for inputs without a gradient (the default) / always zero-padded."""
+    from fcdgan_b200 import engine as E
+    E.set_im2col(request.param)
+    yield request.param
+    E.set_im2col(True)
+
+
+@pytest.mark.parametrize("d_first_layer_form", [False, True], indirect=True)
 @pytest.mark.parametrize("kind", ["usss", "rsss", "wsss"])
-def test_lean_steps_give_the_optimizers_the_same_gradients(kind):
+def test_lean_steps_give_the_optimizers_the_same_gradients(kind, d_first_layer_form):
     """`lean=True` skips only the backward sweeps whose results the reference's loop body throws away (steps.py docstring):
     losses, the change-density map and the BatchNorm running statistics are those of the faithful call sequence, and
-    every network receives the same gradient at the point where its optimizer step consumes it; with optimizers attached the
-    updated parameters agree."""
+    every network receives the same gradient at the point where its optimizer step consumes it.
+
+    Two forms.  With the Discriminator's first layer on ONE code path (zero-padded, `set_im2col(False)`) lean and faithful run
+    the same arithmetic on the same numbers and must agree ELEMENT-WISE to the weight-gradient reductions' atomics noise (2e-4
+    of the largest gradient): this is the test of WHICH sweeps are skipped.  In the default configuration the lean D update
+    feeds D inputs without a gradient, so its first layer runs on receptive-field-packed rows instead: same numbers going in,
+    other summation order, i.e. pre-activations that differ in the last bit.  On these golden tiles (32 x 32) D's deep weight
+    gradients are sums over 2 x 2 x 2 x 2 = 16 positions, so ONE LeakyReLU input that sits within rounding of zero and lands
+    on the other side of the kink moves individual gradient elements by several per cent (measured: 6e-2 of the largest
+    element of `net.8.weight`, deterministically for a given change-density map, 0 for most maps); the bulk of every tensor
+    is unaffected, so this form is held to 2e-2 in the relative L2 norm per tensor."""
+    tol, l2 = (2e-2, True) if d_first_layer_form else (2e-4, False)
     f = load_golden({"usss": "step_usss.pt", "rsss": "step_rsss.pt", "wsss": "step_wsss.pt"}[kind])
     C = f["C"]
     res = {}
@@ -236,7 +260,7 @@ def test_lean_steps_give_the_optimizers_the_same_gradients(kind):
     for k, v in out0.items():                      # every loss and the change-density map: the forward passes are the same
         assert torch.equal(v.detach(), out1[k].detach()) or rel_err(out1[k], v) < 1e-6, k
     for a, b, name in zip(g1, g0, ("first trained network", "second trained network")):
-        _same_grads(a, b, f"{kind} {name}")
+        _same_grads(a, b, f"{kind} {name}", tol, l2)
     # running statistics: bit-identical for G and S (same forward passes); D's first layer runs on receptive-field-packed rows
     # when its inputs carry no gradient (the lean D update) and on the zero-padded form otherwise: same numbers to rounding
     for k in st0:
