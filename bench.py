@@ -64,10 +64,10 @@ GF_PER_PAIR = 227.3
 # committed `ncu --set full` captures named here (B = 16, 256 x 256, 64 -> 64, parity) — NOT measured by this run: `roofline.traffic_source`
 # says so in the JSON line.
 NCU_TRAFFIC_BYTES = {
-    "conv_wgrad_tc 3x3s1 64->64": (544.0e6, "profiles/r02_ncu_full_kernels_summary.txt"),      # 537.1 MB read + 7.0 MB written
-    "conv_fwd_tc 3x3s1 64->64": (492.7e6, "profiles/r02_ncu_full_conv_fwd_stats.txt"),          # 268.8 + 223.9
+    "conv_wgrad_tc 3x3s1 64->64": (542.5e6, "profiles/r02_ncu_full_kernels_summary.txt"),      # 537.0 MB read + 5.4 MB written
+    "conv_fwd_tc 3x3s1 64->64": (495.5e6, "profiles/r02_ncu_full_kernels_summary.txt"),          # 268.7 + 226.9 (conv_halo_kernel)
     "conv_dgrad_tc 3x3s1 64->64": (493.9e6, "profiles/r01_ncu_full_conv_engines_final.txt"),
-    "fcd_bn_act_bwd_apply": (774.2e6, "profiles/r02_ncu_full_kernels_summary.txt"),             # 536.9 + 237.3
+    "fcd_bn_act_bwd_apply": (774.9e6, "profiles/r02_ncu_full_kernels_summary.txt"),             # 536.9 + 238.0
 }
 
 
