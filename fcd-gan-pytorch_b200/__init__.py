@@ -10,8 +10,8 @@ no CPU fallback — constructing modules works anywhere, calling them needs a B2
 """
 __version__ = "0.1.0"
 
-from .engine import (get_precision, get_streams, invalidate_weight_cache, set_precision, set_streams,  # noqa: F401
-                     set_sync_bn)
+from .engine import (get_precision, get_streams, invalidate_weight_cache, set_batch_branches, set_precision,  # noqa: F401
+                     set_rowpack, set_streams, set_sync_bn)
 from .modules import (DoubleConv, Discriminator_SRGAN_simple, Down, Generator, OutConv, ResidualBlock,  # noqa: F401
                       Segmentor, Up)
 from .losses import (CGeneratorLoss, CNetLoss, PerceptionLoss, mean, mean_abs, mean_sq, region_loss,  # noqa: F401
