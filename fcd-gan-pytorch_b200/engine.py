@@ -29,13 +29,13 @@ BN_EPS = 1e-5        # nn.BatchNorm2d defaults relied on by Module.py:27,30,156,
 BN_MOMENTUM = 0.1
 
 _cfg = {"split": True, "engine": ENGINE_AUTO, "fuse_stats": True, "im2col": True, "streams": 1, "sync_bn": None,
-        "batch_branches": True, "rowpack": True}
+        "batch_branches": True, "rowpack": True, "zero_pool": True}
 # A/B switches without code changes: FCD_ENGINE="rowpack=0,batch_branches=0" (bench.py reports the dictionary in its line)
 import os as _os
 
 for _item in filter(None, _os.environ.get("FCD_ENGINE", "").split(",")):
     _k, _, _v = _item.partition("=")
-    if _k.strip() not in ("rowpack", "batch_branches", "im2col", "fuse_stats"):
+    if _k.strip() not in ("rowpack", "batch_branches", "im2col", "fuse_stats", "zero_pool"):
         raise ValueError(f"FCD_ENGINE: unknown switch {_k!r}")
     _cfg[_k.strip()] = bool(int(_v or 1))
 
@@ -496,6 +496,8 @@ class Tape:
         """Zero-initialised float64 tensor for a kernel's atomics / sums (BatchNorm statistics, backward reductions), carved
         from a pool that is filled once per block: a pass needed one tiny fill kernel per convolution and per BatchNorm
         backward.  Slices are never handed out twice (a replayed tape gets fresh zeros), 16-byte aligned."""
+        if not _cfg["zero_pool"]:
+            return torch.zeros(shape, dtype=torch.float64, device=self.device)
         n = 1
         for d in shape:
             n *= d

@@ -146,15 +146,23 @@ def _graph_replay_matches_eager(form):
         assert abs(dl.item() - eager_losses[i][1]) <= t * max(1.0, abs(eager_losses[i][1])), (form, i, dl.item(), eager_losses[i], spread)
     # Adam's / RMSprop's first steps move every element by ~lr (10 lr for RMSprop) * sign(gradient): an element whose gradient
     # is at the level of the weight-gradient reductions' atomic-order noise may take the other sign, so a few elements per tensor
-    # can legitimately differ by a couple of step sizes.  The loss trajectory above is the tight check; here the bulk of every
-    # large tensor must agree tightly and nothing may move further than a few optimizer steps.
+    # can legitimately differ by a couple of step sizes.  And ~3 % of all EAGER runs of this very iteration take a second,
+    # reproducible trajectory (scripts/eager_probe2.py, profiles/r02_eager_trajectory_modes.log: 13 of 582 runs, same numbers
+    # every time, with or without the round-2 engine switches): the siamese discriminator's conv gradients are differences of
+    # two nearly cancelling branch terms (y = x + 0.3 noise), one LeakyReLU input of its last layer sits within atomics noise
+    # of zero in the second iteration, and when it lands on the other side of the kink — same forward, same losses to 1e-7,
+    # same classifier gradients — those gradients change by 10 % in the relative L2 norm, after which ~90 % of the
+    # discriminator's elements differ by a fraction of an optimizer step.  So: the loss trajectory above is the tight check;
+    # here nothing may move further than a few optimizer steps and the bulk of every large tensor must stay within two
+    # (1e-3 = 2 x 10 lr of RMSprop, 5 x lr of Adam).  A graph that replays stale gradients or optimizer state takes the other
+    # sign on ~half of the elements in every step and fails both.
     for (k, got), (_, ref) in zip(_params(netG, netD), want):
         diff = (got - ref).abs()
         assert diff.max().item() <= 5e-3, f"{k}: max |diff| {diff.max().item():.3g}"
         if ref.numel() >= 4096:
-            off = (diff > 1e-6 + 1e-4 * ref.abs()).float().mean().item()
-            # measured over repeated runs: 0 ... 3.4 % of a tensor's elements (those whose gradient is at the atomics' noise level)
-            assert off < 1e-1, f"{k}: {off:.2%} of the elements differ"
+            off = (diff > 1e-3).float().mean().item()
+            # measured: 0 ... 0.5 % on the common trajectory, <= 3 % when one run took the other one
+            assert off < 1e-1, f"{k}: {off:.2%} of the elements differ by more than two optimizer steps"
 
 
 @pytest.mark.parametrize("form", ["whole", "segmented"])
