@@ -7,7 +7,8 @@ device memory (caching allocator), the current stream and the autograd hook (`Ne
 
 Tensors
   * `Act`  split activation: two bf16 NHWC planes (hi, lo), value = hi + lo (lo is None in "fast" precision).
-           Convolution operands.  May be a channel slice of a concatenation buffer (pitch `ld` > Cp).
+           Convolution operands.  May be a channel slice of a concatenation buffer (pitch `ld` > Cp) or the images of one
+           siamese branch inside a batch that carries both (`batch_view`).
   * `Z`    raw convolution output, fp32 NHWC, plus the per-channel sum / sum-of-squares for BatchNorm.
   * gradients w.r.t. an `Act` are fp32 NHWC (`Act.grad`), gradients w.r.t. a `Z` are split (`Z.dz`), because
     they are the operands of the dgrad / wgrad convolutions.

@@ -301,7 +301,7 @@ class Generator(nn.Module):
             training = self.training
             W = inputs[0].shape[3]
             if self.n_channels <= 16 and not need[0]:
-                # 13-band head on the 4-pixel channel-packed input (3 taps of K = 64 per filter row instead of 9)
+                # few-band head on the channel-packed input: one K = pad64(9 C) tap per filter row (13 bands: 117 -> 128) instead of 9
                 a = None
                 xp = E.PackedAct(inputs[0], P=E.row_pack_pixels(self.n_channels, 9))
                 z = E.conv_small_in(tape, xp, self.block1[0].weight, self.block1[0].bias, 4, stats=False)
