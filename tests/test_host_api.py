@@ -198,3 +198,48 @@ def test_any_optimizer_step_invalidates_the_packed_weight_cache():
         e0 = E._weight_epoch
         opt.step()
         assert E._weight_epoch > e0
+
+
+def test_tape_zero_pool_hands_out_disjoint_aligned_zeroed_slices():
+    """engine.Tape.zeros64: accumulators carved from one zero-filled pool per block — never handed out twice (a replayed tape gets
+    fresh zeros), 16-byte aligned, a new block when one is exhausted or a request is larger than a block."""
+    import torch
+    from fcdgan_b200 import engine as E
+    tape = E.Tape(torch.device("cpu"), True)
+    a = tape.zeros64(2, 72)
+    b = tape.zeros64(3)                      # odd count: the next slice must still start on a 16-byte boundary
+    c = tape.zeros64(2, 2, 64)
+    for t in (a, b, c):
+        assert t.dtype == torch.float64 and t.is_contiguous() and float(t.abs().sum()) == 0.0 and t.data_ptr() % 16 == 0
+    a.fill_(1.0); b.fill_(2.0); c.fill_(3.0)
+    assert float(a.sum()) == 144.0 and float(b.sum()) == 6.0 and float(c.sum()) == 3.0 * 256      # no overlap
+    first = tape._arena
+    big = tape.zeros64(E.Tape.ARENA + 2)     # larger than a block: its own block
+    assert tape._arena is not first and float(big.abs().sum()) == 0.0 and big.numel() == E.Tape.ARENA + 2
+    d = tape.zeros64(8)
+    assert float(d.abs().sum()) == 0.0 and float(a.sum()) == 144.0                                 # earlier slices untouched
+    E._cfg["zero_pool"] = False
+    try:
+        e = tape.zeros64(2, 8)
+        assert e.shape == (2, 8) and float(e.abs().sum()) == 0.0
+    finally:
+        E._cfg["zero_pool"] = True
+
+
+def test_act_batch_view_shares_data_and_gradient_with_its_parent():
+    """engine.Act.batch_view: the images of one siamese branch inside the 2B batch the Discriminator's convolutions run on —
+    data and gradient are slices of the parent's buffers (no copies), readiness follows the parent."""
+    import torch
+    from fcdgan_b200 import engine as E
+    h = E.Act.empty(4, 3, 5, 64, torch.device("cpu"))
+    fx, fy = h.batch_view(0, 2), h.batch_view(2, 2)
+    assert fx.hi.data_ptr() == h.hi.data_ptr() and fy.hi.data_ptr() == h.hi[2:].data_ptr()
+    assert (fx.N, fx.H, fx.W, fx.Cp, fx.ld) == (2, 3, 5, 64, 64)
+    fy.grad.fill_(7.0)
+    fx.grad.fill_(1.0)
+    assert float(h.grad[:2].mean()) == 1.0 and float(h.grad[2:].mean()) == 7.0
+    assert not fx.ready
+    h.mark_ready()
+    assert fx.ready and fy.ready
+    h.reset_grad(); fx.reset_grad(); fy.reset_grad()
+    assert fx.grad.data_ptr() == h.grad.data_ptr()          # a new replay: the views follow the parent's NEW gradient buffer
