@@ -149,9 +149,10 @@ def _graph_replay_matches_eager(form):
     # can legitimately differ by a couple of step sizes.  And ~3 % of all EAGER runs of this very iteration take a second,
     # reproducible trajectory (scripts/eager_probe2.py, profiles/r02_eager_trajectory_modes.log: 13 of 582 runs, same numbers
     # every time, with or without the round-2 engine switches): the siamese discriminator's conv gradients are differences of
-    # two nearly cancelling branch terms (y = x + 0.3 noise), one LeakyReLU input of its last layer sits within atomics noise
-    # of zero in the second iteration, and when it lands on the other side of the kink — same forward, same losses to 1e-7,
-    # same classifier gradients — those gradients change by 10 % in the relative L2 norm, after which ~90 % of the
+    # two nearly cancelling branch terms (y = x + 0.3 noise); in the second iteration of those runs the forward pass, the
+    # losses (to 1e-7) and the classifier's gradients are the same, but from the last BatchNorm + LeakyReLU downwards the conv
+    # gradients are 10 % apart in the relative L2 norm — the signature of one LeakyReLU input within atomics noise of zero
+    # landing on the other side of the kink (derivative 0.2 vs 1, forward unchanged) — after which ~90 % of the
     # discriminator's elements differ by a fraction of an optimizer step.  So: the loss trajectory above is the tight check;
     # here nothing may move further than a few optimizer steps and the bulk of every large tensor must stay within two
     # (1e-3 = 2 x 10 lr of RMSprop, 5 x lr of Adam).  A graph that replays stale gradients or optimizer state takes the other
